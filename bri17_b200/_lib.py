@@ -1,0 +1,72 @@
+"""ctypes binding of the C ABI declared in include/bri17_b200.h.
+
+There is deliberately no fallback: if the shared library is missing or a call
+fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libbri17_b200.so")
+
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED = range(5)
+
+_i32p = C.POINTER(C.c_int)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/bri17_b200.h one to one
+SIGNATURES = {
+    "bri17_last_error": (C.c_char_p, []),
+    "bri17_version": (C.c_int, []),
+    "bri17_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, _i32p, _f64p, C.c_double, C.c_double, C.c_int]),
+    "bri17_plan_destroy": (C.c_int, [_vp]),
+    "bri17_plan_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "bri17_plan_get_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
+    "bri17_plan_get_tables": (C.c_int, [_vp, C.c_int, _f64p, _f64p, _f64p, _f64p, _f64p]),
+    "bri17_modal_stiffness_mode_f64": (C.c_int, [_vp, _i32p, _f64p]),
+    "bri17_modal_strain_displacement_mode_f64": (C.c_int, [_vp, _i32p, _f64p]),
+    "bri17_modal_stiffness_apply_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_double, _vp]),
+    "bri17_modal_stiffness_apply_host_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_double]),
+    "bri17_modal_stiffness_field_f64": (C.c_int, [_vp, _vp, _i32p, _i32p, _vp]),
+    "bri17_modal_strain_displacement_field_f64": (C.c_int, [_vp, _vp, _i32p, _i32p, _vp]),
+    "bri17_strain_displacement_apply_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_int64, C.c_double, _vp]),
+    "bri17_freq_index_map": (C.c_int, [_vp, _vp, _i32p, _i32p, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libbri17_b200.so and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m bri17_b200.build` "
+            "(nvcc, sm_100a). bri17_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+class Bri17Error(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    """Translate a status code the way the C++ wrapper does (bri17.hpp errors):
+    invalid argument -> ValueError (std::invalid_argument), else RuntimeError."""
+    if rc == OK:
+        return
+    msg = load().bri17_last_error().decode()
+    if rc == ERR_INVALID_ARG:
+        raise ValueError(msg)
+    raise Bri17Error(f"[bri17_b200 error {rc}] {msg}")

@@ -1,0 +1,131 @@
+// internal.h -- shared declarations of libbri17_b200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "bri17_b200.h"
+
+namespace bri17b200 {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define BRI17_CUDA_TRY(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return ::bri17b200::fail(BRI17_ERR_CUDA, std::string(#expr) + ": " +          \
+                                                   cudaGetErrorString(_e));         \
+  } while (0)
+
+// ---- per-axis tables ----------------------------------------------------------
+// Device layout of one axis: five arrays of N doubles, back to back:
+//   phi | chi | psi | c | s        (bri17.hpp:261-263 and :220-221)
+enum { TAB_PHI = 0, TAB_CHI = 1, TAB_PSI = 2, TAB_C = 3, TAB_S = 4, TAB_COUNT = 5 };
+
+struct AxisTables {
+  std::vector<double> host;  // TAB_COUNT * n
+  double *dev = nullptr;     // same layout
+  int n = 0;
+  const double *h(int which) const { return host.data() + size_t(which) * n; }
+};
+
+// A row-major block of frequencies, normalised to 3 memory dimensions
+// (2-D grids get a leading dimension of extent 1 ... see make_block()).
+struct Block {
+  int dim;
+  int n[3];         // local extents, slowest -> fastest (dim entries used)
+  int kb[3];        // first frequency along each axis
+  int64_t modes;    // prod(n)
+};
+
+// Everything a kernel needs to walk a block tile by tile.  Passed by value.
+struct TileGeom {
+  long long n_rows;    // product of all extents but the fastest
+  long long n_tiles;   // n_rows * cpr
+  int n_inner;         // fastest extent
+  int n_mid;           // 3-D: extent of the middle axis (row = a*n_mid + b); 2-D: 1
+  int n_outer;         // extent of the slowest axis
+  int cpr;             // tiles ("chunks") per row
+  int kb_outer;        // k_begin of the slowest axis
+  int kb_mid;          // k_begin of the middle axis (3-D)
+  int kb_inner;        // k_begin of the fastest axis
+  // per-iteration increments of a persistent CTA (grid stride = gridDim.x tiles)
+  long long d_row;     // gridDim.x / cpr
+  int d_chunk;         // gridDim.x % cpr
+  int d_a, d_b;        // d_row / n_mid, d_row % n_mid
+};
+
+struct ApplyParams {
+  const double2 *u;
+  double2 *f;
+  long long u_stride;   // complex elements between input components
+  long long f_stride;   // ... between output components
+  TileGeom g;
+  const double *tab_outer;  // device tables of the slowest axis
+  const double *tab_mid;    // middle axis (3-D only)
+  const double *tab_inner;  // fastest axis
+  int N_outer, N_mid, N_inner;  // table lengths (global shape)
+  double mu, scaling, out_scale;
+  int stage_outer;      // outer/mid tables of the local range are staged in smem
+};
+
+struct Variant {
+  const char *name;
+  int threads;
+  int vec;           // modes per thread per tile
+  int min_blocks;    // __launch_bounds__ minBlocksPerSM
+  int load_hint;     // 0 default, 1 ld.global.cs, 2 ld.global.nc, 3 nc + L1::no_allocate
+  int store_hint;    // 0 default, 1 st.global.cs
+};
+
+}  // namespace bri17b200
+
+struct bri17_plan {
+  int dim = 0;
+  int shape[3] = {1, 1, 1};
+  double L[3] = {1, 1, 1};
+  double mu = 0, nu = 0;
+  double scaling = 0;  // mu / (1 - 2 nu), bri17.hpp:266
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  bri17b200::AxisTables tab[3];
+  int apply_variant = -1;  // -1: default
+  int64_t host_chunk_rows = 0;
+  int host_streams = 3;
+  // staging for the host-buffer path (lazily allocated, owned by the plan)
+  struct HostStage {
+    cudaStream_t stream = nullptr;
+    void *in = nullptr, *out = nullptr;
+  };
+  std::vector<HostStage> stages;
+  int64_t stage_bytes = 0;
+  int64_t last_grid = 0, last_block = 0, last_smem = 0, launches = 0;
+};
+
+namespace bri17b200 {
+
+int make_block(const bri17_plan *p, const int *k_begin, const int *local_shape, Block *b);
+int num_variants();
+const Variant &variant(int i);
+int default_variant(const bri17_plan *p);
+
+int launch_apply(bri17_plan *p, const Block &b, const void *u, void *f, int64_t u_stride,
+                 int64_t f_stride, double out_scale, cudaStream_t stream);
+int launch_index_map(bri17_plan *p, const Block &b, int32_t *k_out, cudaStream_t stream);
+int launch_stiffness_field(bri17_plan *p, const Block &b, void *K, cudaStream_t stream);
+int launch_strain_field(bri17_plan *p, const Block &b, void *B, cudaStream_t stream);
+int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
+                        int64_t u_stride, int64_t e_stride, double out_scale,
+                        cudaStream_t stream);
+int apply_host(bri17_plan *p, const Block &b, const void *u_host, void *f_host,
+               int64_t comp_stride, double out_scale);
+void free_host_stages(bri17_plan *p);
+
+}  // namespace bri17b200

@@ -1,0 +1,600 @@
+// modal_kernels.cu -- hand-written sm_100a kernels of the modal operator path.
+//
+// K1/K2  modal_stiffness_apply<DIM>   f^[k] = K^[k] u^[k] for every frequency of a block
+//                                     (replaces the loop nest of tests/test_bri17.cpp:58-92;
+//                                      K^ per bri17.hpp:247-292, regenerated per mode in registers)
+// K3     strain_displacement_*        B^[k] field and eps^ = sym(B^ (x) u^) (bri17.hpp:212-236,
+//                                      tests/test_bri17.cpp:194-235)
+// K6     freq_index_map               the multi-index every thread derives (parity check)
+//        modal_stiffness_field        K^[k] written out mode by mode (diagnostic)
+//
+// Design:
+//  * HBM-bound streaming: 96 B/mode (3-D) and 64 B/mode (2-D) of algorithmic
+//    traffic, ~45 FP64 instructions per mode.  No tensor cores, no GEMM shape.
+//  * Persistent CTAs (grid = SMs x resident CTAs) walk (row, chunk) tiles with
+//    a division-free cursor; a row is one line of the fastest axis, so every
+//    128-bit access of a warp is one contiguous 512-byte run per component.
+//  * A CTA keeps the same chunk of the fastest axis from one row to the next,
+//    so the fastest-axis phi/chi/psi of its columns stay in REGISTERS; the
+//    tables of the slower axes are staged once per CTA in shared memory and
+//    read as broadcasts, six doubles per row.
+//  * All loads of a tile are issued before the first use (VEC x DIM
+//    independent 16-byte loads per thread in flight).
+//  * Arithmetic uses __dmul_rn/__dadd_rn in the reference's written order, so
+//    no multiply-add is contracted and the result is bit-identical to the
+//    reference compiled without FMA (the oracle's parity build).
+#include <cstdio>
+
+#include "internal.h"
+
+namespace bri17b200 {
+
+// ---------------------------------------------------------------------------
+// memory access helpers
+// ---------------------------------------------------------------------------
+template <int HINT>
+__device__ __forceinline__ double2 ld_c128(const double2 *p) {
+  if constexpr (HINT == 1) {
+    return __ldcs(p);  // ld.global.cs: streaming, evict first
+  } else if constexpr (HINT == 2) {
+    return __ldg(p);  // ld.global.nc
+  } else if constexpr (HINT == 3) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p));
+    return v;
+  } else if constexpr (HINT == 4) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p));
+    return v;
+  } else {
+    return *p;
+  }
+}
+
+template <int HINT>
+__device__ __forceinline__ void st_c128(double2 *p, double2 v) {
+  if constexpr (HINT == 1) {
+    __stcs(p, v);  // st.global.cs
+  } else if constexpr (HINT == 2) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y)
+                 : "memory");
+  } else {
+    *p = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// tile cursor: which (row, chunk) a persistent CTA works on, and the
+// frequency indices that go with it.  Shared by every kernel in this file, so
+// the index map kernel (K6) tests the mapping the apply kernels use.
+// ---------------------------------------------------------------------------
+struct TileCursor {
+  long long tile;
+  long long row;  // row-major index over all axes but the fastest
+  int chunk;      // which TILE-wide piece of the row
+  int a, b;       // row = a * n_mid + b
+
+  __device__ __forceinline__ void init(const TileGeom &g) {
+    tile = blockIdx.x;
+    row = tile / g.cpr;
+    chunk = int(tile - row * g.cpr);
+    a = int(row / g.n_mid);
+    b = int(row - (long long)a * g.n_mid);
+  }
+  __device__ __forceinline__ bool valid(const TileGeom &g) const { return tile < g.n_tiles; }
+  __device__ __forceinline__ void next(const TileGeom &g) {
+    tile += gridDim.x;
+    row += g.d_row;
+    chunk += g.d_chunk;
+    a += g.d_a;
+    b += g.d_b;
+    if (chunk >= g.cpr) { chunk -= g.cpr; row++; b++; }
+    if (b >= g.n_mid) { b -= g.n_mid; a++; }
+  }
+};
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+
+// Shared-memory staging of the slow-axis tables (local range only).
+// Layout: [phi|chi|psi] of the outer axis (n_outer each), then of the mid axis.
+struct SlowTables {
+  const double *outer;  // phi at [0,n), chi at [n,2n), psi at [2n,3n); n = stride_o
+  const double *mid;
+  int stride_o, stride_m;
+  int off_o, off_m;  // index of local 0 in the arrays
+};
+
+template <int DIM>
+__device__ __forceinline__ SlowTables stage_slow_tables(const ApplyParams &p, double *smem,
+                                                        int n_outer_local) {
+  SlowTables t;
+  if (p.stage_outer) {
+    const int no = n_outer_local, nm = DIM == 3 ? p.g.n_mid : 0;
+    for (int i = threadIdx.x; i < 3 * no; i += blockDim.x) {
+      const int w = i / no, k = i - w * no;
+      smem[i] = p.tab_outer[size_t(w) * p.N_outer + p.g.kb_outer + k];
+    }
+    if constexpr (DIM == 3) {
+      for (int i = threadIdx.x; i < 3 * nm; i += blockDim.x) {
+        const int w = i / nm, k = i - w * nm;
+        smem[3 * no + i] = p.tab_mid[size_t(w) * p.N_mid + p.g.kb_mid + k];
+      }
+    }
+    __syncthreads();
+    t.outer = smem; t.stride_o = no; t.off_o = 0;
+    t.mid = smem + 3 * no; t.stride_m = nm; t.off_m = 0;
+  } else {  // tables too large for the smem budget: read-only L1/L2 path
+    t.outer = p.tab_outer; t.stride_o = p.N_outer; t.off_o = p.g.kb_outer;
+    t.mid = p.tab_mid; t.stride_m = p.N_mid; t.off_m = p.g.kb_mid;
+  }
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// K1 / K2: modal stiffness apply
+// ---------------------------------------------------------------------------
+template <int DIM, int THREADS, int VEC, int MINB, int LDH, int STH>
+__global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_kernel(const ApplyParams p) {
+  extern __shared__ double smem[];
+  constexpr int TILE = THREADS * VEC;
+  const TileGeom &g = p.g;
+  const SlowTables st = stage_slow_tables<DIM>(p, smem, g.n_outer);
+
+  const double mu = p.mu, scaling = p.scaling;
+  const bool scale_out = p.out_scale != 1.0;
+
+  TileCursor cur;
+  cur.init(g);
+  int cached_chunk = -1;
+  int col[VEC];
+  bool ok[VEC];
+  double phiI[VEC], chiI[VEC], psiI[VEC];  // fastest-axis table entries of my columns
+
+  for (; cur.valid(g); cur.next(g)) {
+    if (cur.chunk != cached_chunk) {  // CTA-uniform; taken once when gridDim.x % cpr == 0
+      cached_chunk = cur.chunk;
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        col[j] = cur.chunk * TILE + j * THREADS + threadIdx.x;
+        ok[j] = col[j] < g.n_inner;
+        const int k = g.kb_inner + (ok[j] ? col[j] : 0);
+        phiI[j] = __ldg(p.tab_inner + size_t(TAB_PHI) * p.N_inner + k);
+        chiI[j] = __ldg(p.tab_inner + size_t(TAB_CHI) * p.N_inner + k);
+        psiI[j] = __ldg(p.tab_inner + size_t(TAB_PSI) * p.N_inner + k);
+      }
+    }
+
+    // ---- issue every load of the tile first ----
+    const long long base = cur.row * g.n_inner;
+    double2 u[VEC][DIM];
+#pragma unroll
+    for (int j = 0; j < VEC; j++)
+#pragma unroll
+      for (int c = 0; c < DIM; c++)
+        if (ok[j]) u[j][c] = ld_c128<LDH>(p.u + c * p.u_stride + base + col[j]);
+
+    // ---- row invariants (broadcast reads) ----
+    const int ia = st.off_o + cur.a;
+    const double p0 = st.outer[ia], c0 = st.outer[st.stride_o + ia], s0 = st.outer[2 * st.stride_o + ia];
+
+    if constexpr (DIM == 3) {
+      const int ib = st.off_m + cur.b;
+      const double p1 = st.mid[ib], c1 = st.mid[st.stride_m + ib], s1 = st.mid[2 * st.stride_m + ib];
+      // bri17.hpp:276-288, factors that do not depend on the fastest axis
+      const double h00r = mul(p0, c1);            // phi0*chi1
+      const double h11r = mul(c0, p1);            // chi0*phi1
+      const double h22r = mul(c0, c1);            // chi0*chi1
+      const double k01r = mul(mul(scaling, s0), s1);  // scaling*psi0*psi1
+      const double k02r = mul(mul(scaling, s0), c1);  // scaling*psi0*chi1
+      const double k12r = mul(mul(scaling, c0), s1);  // scaling*chi0*psi1
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        if (!ok[j]) continue;
+        const double H00 = mul(h00r, chiI[j]);                 // :276
+        const double H11 = mul(h11r, chiI[j]);                 // :277
+        const double H22 = mul(h22r, phiI[j]);                 // :278
+        const double Kd = mul(mu, add(add(H00, H11), H22));    // :279
+        const double K00 = add(mul(scaling, H00), Kd);         // :280
+        const double K11 = add(mul(scaling, H11), Kd);         // :284
+        const double K22 = add(mul(scaling, H22), Kd);         // :288
+        const double K01 = mul(k01r, chiI[j]);                 // :281
+        const double K02 = mul(k02r, psiI[j]);                 // :282
+        const double K12 = mul(k12r, psiI[j]);                 // :285
+        const double2 u0 = u[j][0], u1 = u[j][1], u2 = u[j][2];
+        // tests/test_bri17.cpp:84, Im(K)=0, accumulated left to right
+        double2 f0, f1, f2;
+        f0.x = add(add(mul(K00, u0.x), mul(K01, u1.x)), mul(K02, u2.x));
+        f0.y = add(add(mul(K00, u0.y), mul(K01, u1.y)), mul(K02, u2.y));
+        f1.x = add(add(mul(K01, u0.x), mul(K11, u1.x)), mul(K12, u2.x));
+        f1.y = add(add(mul(K01, u0.y), mul(K11, u1.y)), mul(K12, u2.y));
+        f2.x = add(add(mul(K02, u0.x), mul(K12, u1.x)), mul(K22, u2.x));
+        f2.y = add(add(mul(K02, u0.y), mul(K12, u1.y)), mul(K22, u2.y));
+        if (scale_out) {
+          f0.x = mul(f0.x, p.out_scale); f0.y = mul(f0.y, p.out_scale);
+          f1.x = mul(f1.x, p.out_scale); f1.y = mul(f1.y, p.out_scale);
+          f2.x = mul(f2.x, p.out_scale); f2.y = mul(f2.y, p.out_scale);
+        }
+        double2 *o = p.f + base + col[j];
+        st_c128<STH>(o, f0);
+        st_c128<STH>(o + p.f_stride, f1);
+        st_c128<STH>(o + 2 * p.f_stride, f2);
+      }
+    } else {
+      const double k01r = mul(scaling, s0);  // scaling*psi0
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        if (!ok[j]) continue;
+        const double H00 = mul(p0, chiI[j]);               // bri17.hpp:268
+        const double H11 = mul(c0, phiI[j]);               // :269
+        const double Kd = mul(mu, add(H00, H11));          // :270
+        const double K00 = add(mul(scaling, H00), Kd);     // :271
+        const double K01 = mul(k01r, psiI[j]);             // :272
+        const double K11 = add(mul(scaling, H11), Kd);     // :274
+        const double2 u0 = u[j][0], u1 = u[j][1];
+        double2 f0, f1;  // tests/test_bri17.cpp:68
+        f0.x = add(mul(K00, u0.x), mul(K01, u1.x));
+        f0.y = add(mul(K00, u0.y), mul(K01, u1.y));
+        f1.x = add(mul(K01, u0.x), mul(K11, u1.x));
+        f1.y = add(mul(K01, u0.y), mul(K11, u1.y));
+        if (scale_out) {
+          f0.x = mul(f0.x, p.out_scale); f0.y = mul(f0.y, p.out_scale);
+          f1.x = mul(f1.x, p.out_scale); f1.y = mul(f1.y, p.out_scale);
+        }
+        double2 *o = p.f + base + col[j];
+        st_c128<STH>(o, f0);
+        st_c128<STH>(o + p.f_stride, f1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K6: frequency index map (same cursor, THREADS=256, VEC=2 tiles)
+// ---------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) freq_index_map_kernel(const TileGeom g, int32_t *k_out) {
+  constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
+  TileCursor cur;
+  for (cur.init(g); cur.valid(g); cur.next(g)) {
+    const long long base = cur.row * g.n_inner;
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      const int col = cur.chunk * TILE + j * THREADS + threadIdx.x;
+      if (col >= g.n_inner) continue;
+      int32_t *o = k_out + (base + col) * DIM;
+      o[0] = g.kb_outer + cur.a;
+      if constexpr (DIM == 3) {
+        o[1] = g.kb_mid + cur.b;
+        o[2] = g.kb_inner + col;
+      } else {
+        o[1] = g.kb_inner + col;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K^ field (diagnostic): what a loop over Hooke::modal_stiffness would write
+// ---------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) modal_stiffness_field_kernel(const ApplyParams p) {
+  constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
+  const TileGeom &g = p.g;
+  const double mu = p.mu, scaling = p.scaling;
+  double2 *K = p.f;
+  TileCursor cur;
+  for (cur.init(g); cur.valid(g); cur.next(g)) {
+    const long long base = cur.row * g.n_inner;
+    const int ka = g.kb_outer + cur.a;
+    const double p0 = __ldg(p.tab_outer + ka), c0 = __ldg(p.tab_outer + p.N_outer + ka),
+                 s0 = __ldg(p.tab_outer + 2 * size_t(p.N_outer) + ka);
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      const int col = cur.chunk * TILE + j * THREADS + threadIdx.x;
+      if (col >= g.n_inner) continue;
+      const int ki = g.kb_inner + col;
+      const double pI = __ldg(p.tab_inner + ki), cI = __ldg(p.tab_inner + p.N_inner + ki),
+                   sI = __ldg(p.tab_inner + 2 * size_t(p.N_inner) + ki);
+      double2 *o = K + (base + col) * (DIM * DIM);
+      if constexpr (DIM == 3) {
+        const int kb = g.kb_mid + cur.b;
+        const double p1 = __ldg(p.tab_mid + kb), c1 = __ldg(p.tab_mid + p.N_mid + kb),
+                     s1 = __ldg(p.tab_mid + 2 * size_t(p.N_mid) + kb);
+        const double H00 = mul(mul(p0, c1), cI);
+        const double H11 = mul(mul(c0, p1), cI);
+        const double H22 = mul(mul(c0, c1), pI);
+        const double Kd = mul(mu, add(add(H00, H11), H22));
+        const double K00 = add(mul(scaling, H00), Kd);
+        const double K01 = mul(mul(mul(scaling, s0), s1), cI);
+        const double K02 = mul(mul(mul(scaling, s0), c1), sI);
+        const double K11 = add(mul(scaling, H11), Kd);
+        const double K12 = mul(mul(mul(scaling, c0), s1), sI);
+        const double K22 = add(mul(scaling, H22), Kd);
+        o[0] = make_double2(K00, 0.); o[1] = make_double2(K01, 0.); o[2] = make_double2(K02, 0.);
+        o[3] = make_double2(K01, 0.); o[4] = make_double2(K11, 0.); o[5] = make_double2(K12, 0.);
+        o[6] = make_double2(K02, 0.); o[7] = make_double2(K12, 0.); o[8] = make_double2(K22, 0.);
+      } else {
+        const double H00 = mul(p0, cI);
+        const double H11 = mul(c0, pI);
+        const double Kd = mul(mu, add(H00, H11));
+        const double K00 = add(mul(scaling, H00), Kd);
+        const double K01 = mul(mul(scaling, s0), sI);
+        const double K11 = add(mul(scaling, H11), Kd);
+        o[0] = make_double2(K00, 0.); o[1] = make_double2(K01, 0.);
+        o[2] = make_double2(K01, 0.); o[3] = make_double2(K11, 0.);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: strain-displacement.  B^_i = prefactor * s_i * prod_{j != i} c_j with
+// prefactor = (-2 sin S, 2 cos S), S = sum of the half angles (bri17.hpp:224).
+// c/s come from the host tables; sin S / cos S are evaluated with the device
+// sincos on the reference's own argument (the fp64 sum of (pi*k_i)/N_i in the
+// reference's order), the only transcendental evaluated on the GPU.  It is
+// well conditioned (absolute error <= 2 ulp of 1), unlike 1-cos(beta).
+// ---------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ void modal_B(const ApplyParams &p, int ka, int kb, int ki, double2 *B) {
+  constexpr double PI = 3.141592653589793238462643383279502884;
+  const double c0 = __ldg(p.tab_outer + size_t(TAB_C) * p.N_outer + ka);
+  const double s0 = __ldg(p.tab_outer + size_t(TAB_S) * p.N_outer + ka);
+  const double cI = __ldg(p.tab_inner + size_t(TAB_C) * p.N_inner + ki);
+  const double sI = __ldg(p.tab_inner + size_t(TAB_S) * p.N_inner + ki);
+  double sum_alpha = 0.;
+  sum_alpha = add(sum_alpha, __ddiv_rn(mul(PI, double(ka)), double(p.N_outer)));
+  double c1 = 1., s1 = 0.;
+  if constexpr (DIM == 3) {
+    c1 = __ldg(p.tab_mid + size_t(TAB_C) * p.N_mid + kb);
+    s1 = __ldg(p.tab_mid + size_t(TAB_S) * p.N_mid + kb);
+    sum_alpha = add(sum_alpha, __ddiv_rn(mul(PI, double(kb)), double(p.N_mid)));
+  }
+  sum_alpha = add(sum_alpha, __ddiv_rn(mul(PI, double(ki)), double(p.N_inner)));
+  double sn, cs;
+  sincos(sum_alpha, &sn, &cs);
+  const double pre_re = mul(-2., sn), pre_im = mul(2., cs);
+  if constexpr (DIM == 3) {
+    B[0] = make_double2(mul(mul(mul(pre_re, s0), c1), cI), mul(mul(mul(pre_im, s0), c1), cI));
+    B[1] = make_double2(mul(mul(mul(pre_re, c0), s1), cI), mul(mul(mul(pre_im, c0), s1), cI));
+    B[2] = make_double2(mul(mul(mul(pre_re, c0), c1), sI), mul(mul(mul(pre_im, c0), c1), sI));
+  } else {
+    B[0] = make_double2(mul(mul(pre_re, s0), cI), mul(mul(pre_im, s0), cI));
+    B[1] = make_double2(mul(mul(pre_re, c0), sI), mul(mul(pre_im, c0), sI));
+  }
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(add(mul(a.x, b.x), -mul(a.y, b.y)), add(mul(a.x, b.y), mul(a.y, b.x)));
+}
+
+// MODE 0: write B^ (mode-major).  MODE 1: eps^ = sym(B^ (x) u^), planar Mandel.
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(256) strain_displacement_kernel(const ApplyParams p) {
+  constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
+  constexpr int NSYM = DIM * (DIM + 1) / 2;
+  const TileGeom &g = p.g;
+  TileCursor cur;
+  for (cur.init(g); cur.valid(g); cur.next(g)) {
+    const long long base = cur.row * g.n_inner;
+    double2 u[VEC][DIM];
+    int col[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      col[j] = cur.chunk * TILE + j * THREADS + threadIdx.x;
+      if (MODE == 1 && col[j] < g.n_inner)
+#pragma unroll
+        for (int c = 0; c < DIM; c++) u[j][c] = __ldcs(p.u + c * p.u_stride + base + col[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      if (col[j] >= g.n_inner) continue;
+      double2 B[DIM];
+      modal_B<DIM>(p, g.kb_outer + cur.a, g.kb_mid + cur.b, g.kb_inner + col[j], B);
+      if constexpr (MODE == 0) {
+        double2 *o = p.f + (base + col[j]) * DIM;
+#pragma unroll
+        for (int c = 0; c < DIM; c++) o[c] = B[c];
+      } else {
+        // Mandel order: tests/test_bri17.cpp:207-209 (2-D), :224-230 (3-D)
+        constexpr int P3[6] = {0, 1, 2, 1, 2, 0}, Q3[6] = {0, 1, 2, 2, 0, 1};
+        constexpr int P2[3] = {0, 1, 0}, Q2[3] = {0, 1, 1};
+        const double sqrt2 = 1.4142135623730951;  // sqrt(2) rounded to double
+        double2 *o = p.f + base + col[j];
+#pragma unroll
+        for (int s = 0; s < NSYM; s++) {
+          const int pp = DIM == 3 ? P3[s] : P2[s], qq = DIM == 3 ? Q3[s] : Q2[s];
+          const double2 t1 = cmul(B[pp], u[j][qq]);  // :206, :223
+          const double2 t2 = cmul(u[j][pp], B[qq]);
+          double2 e = make_double2(mul(0.5, add(t1.x, t2.x)), mul(0.5, add(t1.y, t2.y)));
+          if (pp != qq) e = make_double2(mul(sqrt2, e.x), mul(sqrt2, e.y));
+          if (p.out_scale != 1.0) e = make_double2(mul(e.x, p.out_scale), mul(e.y, p.out_scale));
+          __stcs(o + s * p.f_stride, e);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: geometry, variants, launchers
+// ---------------------------------------------------------------------------
+static const Variant kVariants[] = {
+    //  name              threads vec minb ld st
+    {"t256v2_cs", 256, 2, 2, 1, 1},       // 0
+    {"t256v2_plain", 256, 2, 2, 0, 0},    // 1
+    {"t256v1_cs", 256, 1, 6, 1, 1},       // 2
+    {"t256v4_cs", 256, 4, 1, 1, 1},       // 3
+    {"t128v2_cs", 128, 2, 4, 1, 1},       // 4
+    {"t128v4_cs", 128, 4, 3, 1, 1},       // 5
+    {"t512v1_cs", 512, 1, 3, 1, 1},       // 6
+    {"t512v2_cs", 512, 2, 1, 1, 1},       // 7
+    {"t256v2_ncna_cs", 256, 2, 2, 3, 1},  // 8
+    {"t256v2_ldg_plain", 256, 2, 2, 2, 0},// 9
+    {"t256v2_na_na", 256, 2, 2, 4, 2},    // 10
+    {"t128v1_cs", 128, 1, 12, 1, 1},      // 11
+    {"t256v1_plain", 256, 1, 6, 0, 0},    // 12
+    {"t256v1_ncna_cs", 256, 1, 6, 3, 1},  // 13
+};
+
+int num_variants() { return int(sizeof(kVariants) / sizeof(kVariants[0])); }
+const Variant &variant(int i) { return kVariants[i]; }
+int default_variant(const bri17_plan *) { return 0; }
+
+typedef void (*ApplyKernel)(const ApplyParams);
+
+template <int DIM>
+static ApplyKernel apply_kernel_for(int v) {
+  switch (v) {
+    case 0: return modal_stiffness_apply_kernel<DIM, 256, 2, 2, 1, 1>;
+    case 1: return modal_stiffness_apply_kernel<DIM, 256, 2, 2, 0, 0>;
+    case 2: return modal_stiffness_apply_kernel<DIM, 256, 1, 6, 1, 1>;
+    case 3: return modal_stiffness_apply_kernel<DIM, 256, 4, 1, 1, 1>;
+    case 4: return modal_stiffness_apply_kernel<DIM, 128, 2, 4, 1, 1>;
+    case 5: return modal_stiffness_apply_kernel<DIM, 128, 4, 3, 1, 1>;
+    case 6: return modal_stiffness_apply_kernel<DIM, 512, 1, 3, 1, 1>;
+    case 7: return modal_stiffness_apply_kernel<DIM, 512, 2, 1, 1, 1>;
+    case 8: return modal_stiffness_apply_kernel<DIM, 256, 2, 2, 3, 1>;
+    case 9: return modal_stiffness_apply_kernel<DIM, 256, 2, 2, 2, 0>;
+    case 10: return modal_stiffness_apply_kernel<DIM, 256, 2, 2, 4, 2>;
+    case 11: return modal_stiffness_apply_kernel<DIM, 128, 1, 12, 1, 1>;
+    case 12: return modal_stiffness_apply_kernel<DIM, 256, 1, 6, 0, 0>;
+    case 13: return modal_stiffness_apply_kernel<DIM, 256, 1, 6, 3, 1>;
+  }
+  return nullptr;
+}
+
+// Tile geometry of a block for tiles of `tile` modes and a grid of at most
+// `max_ctas` persistent CTAs.  Returns the grid size.
+static int make_geom(const Block &b, int tile, int max_ctas, TileGeom *g) {
+  const int dim = b.dim;
+  g->n_inner = b.n[dim - 1];
+  g->n_mid = dim == 3 ? b.n[1] : 1;
+  g->n_outer = b.n[0];
+  g->n_rows = (long long)b.n[0] * g->n_mid;
+  g->cpr = (g->n_inner + tile - 1) / tile;
+  g->n_tiles = g->n_rows * g->cpr;
+  g->kb_outer = b.kb[0];
+  g->kb_mid = dim == 3 ? b.kb[1] : 0;
+  g->kb_inner = b.kb[dim - 1];
+  long long grid = max_ctas;
+  if (grid > g->n_tiles) grid = g->n_tiles;
+  // keep the chunk of a CTA fixed from one row to the next when possible
+  if (grid >= g->cpr) grid -= grid % g->cpr;
+  if (grid < 1) grid = 1;
+  g->d_row = grid / g->cpr;
+  g->d_chunk = int(grid % g->cpr);
+  g->d_a = int(g->d_row / g->n_mid);
+  g->d_b = int(g->d_row % g->n_mid);
+  return int(grid);
+}
+
+static void fill_params(const bri17_plan *p, const Block &b, ApplyParams *ap) {
+  const int dim = b.dim;
+  ap->tab_outer = p->tab[0].dev;
+  ap->N_outer = p->shape[0];
+  ap->tab_mid = dim == 3 ? p->tab[1].dev : p->tab[0].dev;
+  ap->N_mid = dim == 3 ? p->shape[1] : 1;
+  ap->tab_inner = p->tab[dim - 1].dev;
+  ap->N_inner = p->shape[dim - 1];
+  ap->mu = p->mu;
+  ap->scaling = p->scaling;
+  ap->out_scale = 1.0;
+  ap->stage_outer = 0;
+  ap->u = nullptr;
+  ap->f = nullptr;
+  ap->u_stride = ap->f_stride = 0;
+}
+
+static int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(BRI17_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+  return BRI17_OK;
+}
+
+int launch_apply(bri17_plan *p, const Block &b, const void *u, void *f, int64_t u_stride,
+                 int64_t f_stride, double out_scale, cudaStream_t stream) {
+  const int vi = p->apply_variant < 0 ? default_variant(p) : p->apply_variant;
+  const Variant &v = kVariants[vi];
+  ApplyKernel kern = b.dim == 3 ? apply_kernel_for<3>(vi) : apply_kernel_for<2>(vi);
+  if (!kern) return fail(BRI17_ERR_UNSUPPORTED, "unknown apply variant");
+
+  ApplyParams ap;
+  fill_params(p, b, &ap);
+  ap.u = static_cast<const double2 *>(u);
+  ap.f = static_cast<double2 *>(f);
+  ap.u_stride = u_stride;
+  ap.f_stride = f_stride;
+  ap.out_scale = out_scale;
+
+  // shared memory: slow-axis tables of the local range, if they fit 48 KB
+  const int n_outer = b.n[0], n_mid = b.dim == 3 ? b.n[1] : 0;
+  size_t smem = size_t(3) * (n_outer + n_mid) * sizeof(double);
+  if (smem <= 48 * 1024) ap.stage_outer = 1; else smem = 0;
+
+  int occ = 0;
+  BRI17_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, v.threads, smem));
+  if (occ < 1) return fail(BRI17_ERR_CUDA, "apply kernel does not fit on an SM");
+  const int grid = make_geom(b, v.threads * v.vec, p->sm_count * occ, &ap.g);
+
+  kern<<<grid, v.threads, smem, stream>>>(ap);
+  p->last_grid = grid; p->last_block = v.threads; p->last_smem = int64_t(smem);
+  p->launches++;
+  return check_launch("modal_stiffness_apply");
+}
+
+int launch_index_map(bri17_plan *p, const Block &b, int32_t *k_out, cudaStream_t stream) {
+  TileGeom g;
+  const int grid = make_geom(b, 512, p->sm_count * 8, &g);
+  if (b.dim == 3) freq_index_map_kernel<3><<<grid, 256, 0, stream>>>(g, k_out);
+  else freq_index_map_kernel<2><<<grid, 256, 0, stream>>>(g, k_out);
+  p->launches++;
+  return check_launch("freq_index_map");
+}
+
+int launch_stiffness_field(bri17_plan *p, const Block &b, void *K, cudaStream_t stream) {
+  ApplyParams ap;
+  fill_params(p, b, &ap);
+  ap.f = static_cast<double2 *>(K);
+  const int grid = make_geom(b, 512, p->sm_count * 4, &ap.g);
+  if (b.dim == 3) modal_stiffness_field_kernel<3><<<grid, 256, 0, stream>>>(ap);
+  else modal_stiffness_field_kernel<2><<<grid, 256, 0, stream>>>(ap);
+  p->launches++;
+  return check_launch("modal_stiffness_field");
+}
+
+int launch_strain_field(bri17_plan *p, const Block &b, void *B, cudaStream_t stream) {
+  ApplyParams ap;
+  fill_params(p, b, &ap);
+  ap.f = static_cast<double2 *>(B);
+  const int grid = make_geom(b, 512, p->sm_count * 4, &ap.g);
+  if (b.dim == 3) strain_displacement_kernel<3, 0><<<grid, 256, 0, stream>>>(ap);
+  else strain_displacement_kernel<2, 0><<<grid, 256, 0, stream>>>(ap);
+  p->launches++;
+  return check_launch("modal_strain_displacement_field");
+}
+
+int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
+                        int64_t u_stride, int64_t e_stride, double out_scale,
+                        cudaStream_t stream) {
+  ApplyParams ap;
+  fill_params(p, b, &ap);
+  ap.u = static_cast<const double2 *>(u);
+  ap.f = static_cast<double2 *>(eps);
+  ap.u_stride = u_stride;
+  ap.f_stride = e_stride;
+  ap.out_scale = out_scale;
+  const int grid = make_geom(b, 512, p->sm_count * 4, &ap.g);
+  if (b.dim == 3) strain_displacement_kernel<3, 1><<<grid, 256, 0, stream>>>(ap);
+  else strain_displacement_kernel<2, 1><<<grid, 256, 0, stream>>>(ap);
+  p->launches++;
+  return check_launch("strain_displacement_apply");
+}
+
+}  // namespace bri17b200

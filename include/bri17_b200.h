@@ -1,0 +1,164 @@
+/*
+ * bri17_b200.h -- C ABI of libbri17_b200.so, the B200 (sm_100a) implementation
+ * of the bri17 modal operator path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `int` status codes,
+ * no C++/torch types.  The C++ header include/bri17/bri17.hpp
+ * (bri17::ModalOperator) and the Python mirror (bri17_b200/) are thin wrappers
+ * over exactly these entry points; INTEGRATION.md shows the binding a bri17
+ * maintainer would add.
+ *
+ * Reference interfaces replaced (file:line relative to the bri17 repository):
+ *   include/bri17/bri17.hpp:34-58    CartesianGrid<T,DIM>{shape, L}   -> bri17_plan_create(dim, shape, L, ...)
+ *   include/bri17/bri17.hpp:176-194  Hooke<T,DIM>{mu, nu, grid}       -> bri17_plan_create(..., mu, nu, ...)
+ *   include/bri17/bri17.hpp:247-292  Hooke::modal_stiffness(k, K)     -> bri17_modal_stiffness_mode_f64 (one mode, host)
+ *                                                                        bri17_modal_stiffness_field_f64 (every mode, device)
+ *   include/bri17/bri17.hpp:212-236  Hooke::modal_strain_displacement -> bri17_modal_strain_displacement_mode_f64 / _field_f64
+ *   tests/test_bri17.cpp:58-92       loop nest: gather, K^[k]*u^[k], scatter
+ *                                                                     -> bri17_modal_stiffness_apply_f64 (device buffers)
+ *                                                                        bri17_modal_stiffness_apply_host_f64 (host buffers)
+ *   tests/test_bri17.cpp:62-64,71 / :76-79,88   frequency <-> linear index  -> bri17_freq_index_map
+ *   tests/test_bri17.cpp:194-235     strain recovery loop (compute_Bu) -> bri17_strain_displacement_apply_f64
+ *   tests/test_bri17.cpp:56-107      real-space apply (FFT, K^, iFFT, |h|/|N|) -> bri17_real_space_apply_f64
+ *
+ * Data layout (tests/test_bri17.cpp:66-67, :81-83): a field is PLANAR by
+ * component; each component is a row-major block of interleaved complex
+ * doubles (re, im) = std::complex<double> = 16 bytes.  Element (c, i) of a
+ * field lives at base[i + c*comp_stride] (in complex elements).  A "block" is
+ * the set of frequencies k = k_begin + [0, local_shape) -- the whole grid for
+ * the reference's use (k_begin = 0, local_shape = shape), a slab of it for
+ * multi-GPU runs.  Frequencies are raw indices in [0, N_d): no fftshift, no
+ * negative wrap (bri17.hpp:260 uses k as is).
+ *
+ * Ownership: the caller owns and preallocates every buffer (as in
+ * bri17.hpp:207-211, :241-246).  A plan owns only its per-axis tables and, for
+ * the *_host_* entry point, its staging buffers.  Input and output may alias.
+ *
+ * Errors: every function returns BRI17_OK or an error code and never throws;
+ * bri17_last_error() returns a thread-local message.  There is no CPU
+ * fallback: without a CUDA device plan creation fails with BRI17_ERR_CUDA.
+ */
+#ifndef BRI17_B200_H
+#define BRI17_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BRI17_API __attribute__((visibility("default")))
+#else
+#define BRI17_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRI17_VERSION 100 /* 0.1.0, tracks metadata/version.txt of the reference */
+
+enum {
+  BRI17_OK = 0,
+  BRI17_ERR_INVALID_ARG = 1, /* bad dim/shape/pointer/alignment: std::invalid_argument in the C++ wrapper */
+  BRI17_ERR_CUDA = 2,        /* CUDA runtime failure: std::runtime_error */
+  BRI17_ERR_NCCL = 3,        /* NCCL failure (real-space apply only) */
+  BRI17_ERR_UNSUPPORTED = 4
+};
+
+typedef struct bri17_plan bri17_plan;
+
+/* `device` value for a plan that only serves the per-mode HOST API
+ * (bri17_modal_*_mode_f64, bri17_plan_get_tables).  Every whole-grid entry
+ * point fails with BRI17_ERR_CUDA on such a plan: there is no CPU fallback. */
+#define BRI17_DEVICE_NONE (-1)
+
+/* Thread-local description of the last failure on the calling thread. */
+BRI17_API const char *bri17_last_error(void);
+BRI17_API int bri17_version(void);
+
+/*
+ * Create the operator for CartesianGrid{shape, L} + Hooke{mu, nu} on CUDA
+ * device `device` (bri17.hpp:54, :193).  dim is 2 or 3.  Builds the per-axis
+ * tables phi/chi/psi (bri17.hpp:259-263) and c/s (bri17.hpp:218-221) on the
+ * host with libm, in the reference's operation order, and uploads them
+ * (3+2 doubles per grid line: K^ itself is never materialised).
+ */
+BRI17_API int bri17_plan_create(bri17_plan **out, int dim, const int *shape,
+                      const double *L, double mu, double nu, int device);
+BRI17_API int bri17_plan_destroy(bri17_plan *plan);
+
+/* Tuning/diagnostic knobs ("apply_variant", "host_chunk_rows", ...). */
+BRI17_API int bri17_plan_set_option(bri17_plan *plan, const char *key, int64_t value);
+BRI17_API int bri17_plan_get_info(const bri17_plan *plan, const char *key, int64_t *value);
+
+/* Host copy of the tables of one axis; any output pointer may be NULL.
+ * Each array has shape[axis] entries. */
+BRI17_API int bri17_plan_get_tables(const bri17_plan *plan, int axis, double *phi,
+                          double *chi, double *psi, double *c, double *s);
+
+/* ---- one frequency, host side (the reference's per-mode API) ------------- */
+
+/* Hooke::modal_stiffness (bri17.hpp:247-292): K[dim*dim] interleaved complex,
+ * row-major K[dim*i+j], imaginary parts zero.  k[d] must lie in [0, shape[d]). */
+BRI17_API int bri17_modal_stiffness_mode_f64(const bri17_plan *plan, const int *k, double *K);
+/* Hooke::modal_strain_displacement (bri17.hpp:212-236): B[dim] interleaved. */
+BRI17_API int bri17_modal_strain_displacement_mode_f64(const bri17_plan *plan, const int *k, double *B);
+
+/* ---- every frequency of a block, device side ----------------------------- */
+
+/*
+ * f^[c,k] = out_scale * sum_j K^[k][c,j] u^[j,k]   (tests/test_bri17.cpp:58-92)
+ *
+ * u_hat_dev, f_hat_dev: device pointers, 16-byte aligned, planar layout above.
+ * k_begin, local_shape: dim ints each, or NULL for the whole grid.
+ * comp_stride: complex elements between components; 0 means prod(local_shape).
+ * out_scale: 1.0 reproduces the reference bit for bit (no multiply is issued);
+ *            the real-space apply passes |h|/|N| (tests/test_bri17.cpp:98).
+ * stream: a cudaStream_t (NULL = default stream).  Asynchronous.
+ */
+BRI17_API int bri17_modal_stiffness_apply_f64(bri17_plan *plan, const void *u_hat_dev,
+                                    void *f_hat_dev, const int *k_begin,
+                                    const int *local_shape, int64_t comp_stride,
+                                    double out_scale, void *stream);
+
+/*
+ * Same operation on HOST buffers: the block is cut along its slowest axis into
+ * chunks that are copied in, processed and copied out on rotating streams so
+ * that both PCIe directions and the kernel overlap.  Synchronous.  Pinned
+ * (page-locked) buffers give full PCIe bandwidth; pageable memory works too.
+ */
+BRI17_API int bri17_modal_stiffness_apply_host_f64(bri17_plan *plan, const void *u_hat_host,
+                                         void *f_hat_host, const int *k_begin,
+                                         const int *local_shape, int64_t comp_stride,
+                                         double out_scale);
+
+/* K^[k] for every mode of the block, mode-major: K_dev[(i*dim*dim + r*dim + j)]
+ * complex, i the row-major linear index in the block (what a loop over
+ * Hooke::modal_stiffness would write).  144 B/mode in 3-D: diagnostic only. */
+BRI17_API int bri17_modal_stiffness_field_f64(bri17_plan *plan, void *K_dev, const int *k_begin,
+                                    const int *local_shape, void *stream);
+
+/* B^[k] for every mode of the block, mode-major: B_dev[i*dim + j] complex. */
+BRI17_API int bri17_modal_strain_displacement_field_f64(bri17_plan *plan, void *B_dev,
+                                              const int *k_begin, const int *local_shape,
+                                              void *stream);
+
+/*
+ * eps^ = 1/2 (B^ (x) u^ + u^ (x) B^) in Mandel order (tests/test_bri17.cpp:194-235):
+ * 2-D [00, 11, sqrt2*01], 3-D [00, 11, 22, sqrt2*12, sqrt2*20, sqrt2*01];
+ * planar output with eps_stride complex elements between components (0 = dense).
+ */
+BRI17_API int bri17_strain_displacement_apply_f64(bri17_plan *plan, const void *u_hat_dev,
+                                        void *eps_hat_dev, const int *k_begin,
+                                        const int *local_shape, int64_t u_stride,
+                                        int64_t eps_stride, double out_scale, void *stream);
+
+/* Frequency multi-index the kernels derive for every linear element of the
+ * block: k_out_dev[i*dim + d] (int32).  Uses the same tile cursor as the apply
+ * kernels; the parity tests require it to be bit-identical to the reference's
+ * loop nest (tests/test_bri17.cpp:62-64,71 / :76-79,88). */
+BRI17_API int bri17_freq_index_map(bri17_plan *plan, int32_t *k_out_dev, const int *k_begin,
+                         const int *local_shape, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRI17_B200_H */
