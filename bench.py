@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--edge", type=int, default=512, help="grid edge (512 = the BASELINE workload)")
+    ap.add_argument("--dim", type=int, default=3, choices=[2, 3],
+                    help="3 = the BASELINE metric; 2 with --edge 4096 = BASELINE configs[1] (tuning only)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -188,12 +190,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    edge, dim = args.edge, 3
-    plane = edge * edge
+    edge, dim = args.edge, args.dim
     peak, peak_src = peaks()
 
-    # ---- weak-scaled workload: one edge^3 slab per GPU of a (edge*N, edge, edge) grid ----
-    shape = (edge * world, edge, edge)
+    # ---- weak-scaled workload: one edge^dim slab per GPU of a (edge*N, edge[, edge]) grid ----
+    shape = (edge * world,) + (edge,) * (dim - 1)
     L = tuple(n * h for n, h in zip(shape, SPACING))
     op = b.ModalOperator(shape, L, MU, NU, device=local_rank)
     if args.variant >= 0:
@@ -248,7 +249,7 @@ def main():
         for a in sorted({0, local[0] // 2, local[0] - 1}):
             k0 = k_begin[0] + a
             ref = o.apply_modal_stiffness(shape, L, MU, NU, u[:, a:a + 1].cpu().numpy(),
-                                          k_begin=(k0, 0, 0))
+                                          k_begin=(k0,) + (0,) * (dim - 1))
             got = f[:, a:a + 1].cpu().numpy()
             den = np.abs(ref).max(axis=0)
             num = np.abs(got - ref).max(axis=0)
@@ -262,14 +263,14 @@ def main():
     # ---- strong-scaled companion: the edge^3 grid of BASELINE config 3 split over N GPUs ----
     strong = None
     if world > 1:
-        s_shape = (edge, edge, edge)
+        s_shape = (edge,) * dim
         s_L = tuple(n * h for n, h in zip(s_shape, SPACING))
         s_op = b.ModalOperator(s_shape, s_L, MU, NU, device=local_rank)
         s_kb, s_local = slab.rank_block(s_shape, rank, world)
         su, sf = u[:, :s_local[0]].contiguous(), f[:, :s_local[0]].contiguous()
         s_ms = timed(lambda: s_op.apply_modal_stiffness(su, out=sf, k_begin=s_kb), args.steps, args.warmup)
         strong = {"workload": f"3D {edge}^3 split into {world} k0 slabs", "ms_per_step": s_ms,
-                  "value": edge ** 3 / (s_ms * 1e-3) / 1e9, "unit": UNIT, "scaling": "strong"}
+                  "value": edge ** dim / (s_ms * 1e-3) / 1e9, "unit": UNIT, "scaling": "strong"}
         del su, sf
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
@@ -297,8 +298,12 @@ def main():
         del hu, hf
 
     if rank == 0:
+        traffic = None            # DRAM bytes per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath) and edge == {3: 512, 2: 4096}[dim]:
+            traffic = json.load(open(tpath))[str(dim)]["dram_bytes_per_launch"] / 1e9
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and dim == 3 and not args.no_cpu_baseline:
             try:
                 _, _, cpu = cpu_reference_leg(edge, steps=5, warmup=1, target_step_s=3.0)
             except Exception as e:
@@ -307,17 +312,21 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D Q8 {edge}^3 modal stiffness apply per GPU (BASELINE configs[2]); "
-                                   f"global grid {shape[0]}x{shape[1]}x{shape[2]}, one k0 slab per GPU, no comm",
+            "config": {"workload": f"{dim}D Q{1 << dim} {edge}^{dim} modal stiffness apply per GPU "
+                                   f"(BASELINE configs[{dim - 1}]); global grid {'x'.join(map(str, shape))}, "
+                                   "one k0 slab per GPU, no comm",
                        "modes_per_gpu": modes_rank, "mu": MU, "nu": NU, "spacing": SPACING,
                        "l2": "inputs (6 GiB) and outputs (6 GiB) per GPU exceed the 126 MB L2; no flush",
                        "kernel_variant": op.info("apply_variant"), "grid": op.info("last_grid"),
                        "block": op.info("last_block"), "smem": op.info("last_smem")},
             "gdof_per_s": value * dim,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_unit": "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_gb_per_launch": BYTES_PER_MODE[dim] * modes_rank / 1e9,
+                         "peak_source": peak_src,
                          "bytes_per_mode": BYTES_PER_MODE[dim], "modes_per_launch": modes_rank,
-                         "kernel": "modal_stiffness_apply_kernel<3,...>",
+                         "kernel": f"modal_stiffness_apply_kernel<{dim},...>",
                          "timing": "CUDA events on the launch stream around the timed steps / steps"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "parity": parity, "strong_scaling": strong,

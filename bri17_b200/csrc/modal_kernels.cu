@@ -444,7 +444,9 @@ static const Variant kVariants[] = {
 
 int num_variants() { return int(sizeof(kVariants) / sizeof(kVariants[0])); }
 const Variant &variant(int i) { return kVariants[i]; }
-int default_variant(const bri17_plan *) { return 0; }
+// Measured on B200 (profiles/r01_variant_sweep.md): 3-D 512^3 -> t256v2_cs 98.2 % of the measured
+// HBM copy peak; 2-D 4096^2 (1 GiB, 0.17 ms) prefers smaller CTAs -> t128v2_cs 98.5 %.
+int default_variant(const bri17_plan *p) { return p->dim == 2 ? 4 : 0; }
 
 typedef void (*ApplyKernel)(const ApplyParams);
 
