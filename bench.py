@@ -116,7 +116,8 @@ def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None):
     same workload.  Returns (value Gmodes/s, s/step, descr dict)."""
     from oracle import oracle                      # checker/baseline only (see oracle/)
     impl = oracle.best(fast=True)
-    threads = threads or impl.max_threads()
+    # every host thread the process may use; not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    threads = threads or len(os.sched_getaffinity(0))
     shape = (edge, edge, edge)
     L = tuple(n * h for n, h in zip(shape, SPACING))
     plane = edge * edge
