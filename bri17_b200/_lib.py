@@ -21,6 +21,7 @@ _vp = C.c_void_p
 SIGNATURES = {
     "bri17_last_error": (C.c_char_p, []),
     "bri17_version": (C.c_int, []),
+    "bri17_set_last_error": (None, [C.c_char_p]),
     "bri17_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, _i32p, _f64p, C.c_double, C.c_double, C.c_int]),
     "bri17_plan_destroy": (C.c_int, [_vp]),
     "bri17_plan_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
@@ -36,7 +37,44 @@ SIGNATURES = {
     "bri17_freq_index_map": (C.c_int, [_vp, _vp, _i32p, _i32p, _vp]),
 }
 
+# include/bri17_b200_realspace.h (libbri17_b200_rs.so)
+RS_LIB_PATH = os.path.join(HERE, "lib", "libbri17_b200_rs.so")
+RS_SIGNATURES = {
+    "bri17_rs_unique_id": (C.c_int, [_vp]),
+    "bri17_rs_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, _i32p, _f64p, C.c_double, C.c_double,
+                                       C.c_int, C.c_int, C.c_int, _vp, C.c_int]),
+    "bri17_rs_plan_destroy": (C.c_int, [_vp]),
+    "bri17_rs_plan_local": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p]),
+    "bri17_rs_plan_real_count": (C.c_int64, [_vp]),
+    "bri17_rs_plan_fourier_count": (C.c_int64, [_vp]),
+    "bri17_real_space_apply_f64": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bri17_rs_forward_fft_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "bri17_rs_inverse_fft_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, _vp]),
+    "bri17_rs_plan_modal": (_vp, [_vp]),
+    "bri17_rs_plan_last_timings": (C.c_int, [_vp, _f64p, C.c_int]),
+    "bri17_rs_plan_exchange_bytes": (C.c_int64, [_vp]),
+    "bri17_cg_solve_f64": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _i32p, _f64p, _vp]),
+}
+
 _lib = None
+_rs_lib = None
+
+
+def load_rs() -> C.CDLL:
+    """Load libbri17_b200_rs.so (cuFFT + NCCL layer); no fallback."""
+    global _rs_lib
+    if _rs_lib is not None:
+        return _rs_lib
+    load()
+    if not os.path.exists(RS_LIB_PATH):
+        raise RuntimeError(f"{RS_LIB_PATH} is missing: build it with `python -m bri17_b200.build`")
+    lib = C.CDLL(RS_LIB_PATH)
+    for name, (restype, argtypes) in RS_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _rs_lib = lib
+    return lib
 
 
 def load() -> C.CDLL:

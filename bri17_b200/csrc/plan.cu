@@ -89,6 +89,7 @@ extern "C" {
 
 const char *bri17_last_error(void) { return g_last_error.c_str(); }
 int bri17_version(void) { return BRI17_VERSION; }
+void bri17_set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
 
 int bri17_plan_create(bri17_plan **out, int dim, const int *shape, const double *L,
                       double mu, double nu, int device) {

@@ -73,6 +73,9 @@ typedef struct bri17_plan bri17_plan;
 /* Thread-local description of the last failure on the calling thread. */
 BRI17_API const char *bri17_last_error(void);
 BRI17_API int bri17_version(void);
+/* Sets that message; used by companion libraries (libbri17_b200_rs.so) so that
+ * one bri17_last_error() serves every entry point. */
+BRI17_API void bri17_set_last_error(const char *msg);
 
 /*
  * Create the operator for CartesianGrid{shape, L} + Hooke{mu, nu} on CUDA

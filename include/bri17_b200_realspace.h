@@ -1,0 +1,115 @@
+/*
+ * bri17_b200_realspace.h -- C ABI of libbri17_b200_rs.so: the end-to-end
+ * real-space operator and the CG solve built on it.
+ *
+ * Reference interface replaced (file:line in the bri17 repository):
+ *   tests/test_bri17.cpp:56-107   StiffnessMatrixFactory::compute_Ku
+ *        F = (|h|/|N|) * iDFT_unnormalised( K^ . DFT(u) ),  DIM forward and DIM
+ *        backward c2c transforms on the planar component blocks (:117-127,
+ *        FFTW_FORWARD / FFTW_BACKWARD), correction |h|/|N| (:93-106)
+ *   sphinx/theory.rst:60,72,151-157  DFT sign/scale conventions, eqs (1),(3),(11)-(12)
+ *   python/demo.py:11-40 + bri17.hpp:336-341   the periodic inclusion problem
+ *        K^ u^ = tau^ . conj(B^), u^(0) = 0, solved here matrix-free by CG.
+ *
+ * FFTW (serial, host) becomes cuFFT (local transforms) plus a slab
+ * decomposition over `nranks` GPUs, one process per GPU:
+ *
+ *   real space   u[c][n0 in my slab][n1][n2]          (slab over axis 0)
+ *   Fourier      u^[c][k0][k1 in my slab][k2]         (slab over axis 1)
+ *
+ * forward = local FFT over axes 1.. -> all-to-all (slab transpose over
+ * NVLink) -> FFT along axis 0; the modal operator runs directly on the
+ * Fourier-side block (k_begin = {0, k1_begin, 0}), then the inverse path.
+ * The all-to-all is either NCCL grouped send/recv with a pack/unpack kernel
+ * on the strided side (mode 0), or ONE kernel per direction that reads the
+ * local slab and stores straight into the peers' buffers through CUDA-IPC
+ * mapped memory, so that the transposition is the transfer (mode 1).
+ *
+ * Layout, ownership and error conventions are those of bri17_b200.h.  Real
+ * fields are carried as complex numbers with zero imaginary part, exactly
+ * like the reference (tests/test_bri17.cpp:133-136).
+ */
+#ifndef BRI17_B200_REALSPACE_H
+#define BRI17_B200_REALSPACE_H
+
+#include <stdint.h>
+
+#include "bri17_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bri17_rs_plan bri17_rs_plan;
+
+#define BRI17_NCCL_UNIQUE_ID_BYTES 128
+
+/* Rank 0 calls this and distributes the 128 bytes to the other ranks (any
+ * transport: torch.distributed, MPI, a file); not needed when nranks == 1. */
+BRI17_API int bri17_rs_unique_id(void *out128);
+
+/*
+ * Collective over the `nranks` processes.  shape[0] and shape[1] are split
+ * into contiguous balanced slabs (rank g owns [g*N/P, (g+1)*N/P)).
+ * exchange_mode: 0 = NCCL send/recv + pack kernels, 1 = fused peer-store kernel.
+ */
+BRI17_API int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const double *L,
+                                   double mu, double nu, int device, int rank, int nranks,
+                                   const void *nccl_unique_id, int exchange_mode);
+BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
+
+/* Geometry of this rank: real-space slab [n0_begin, n0_begin+n0_count) of axis
+ * 0, Fourier-space slab [k1_begin, k1_begin+k1_count) of axis 1. */
+BRI17_API int bri17_rs_plan_local(const bri17_rs_plan *plan, int *n0_begin, int *n0_count,
+                                  int *k1_begin, int *k1_count);
+/* Complex elements per component of the real-space slab / the Fourier slab. */
+BRI17_API int64_t bri17_rs_plan_real_count(const bri17_rs_plan *plan);
+BRI17_API int64_t bri17_rs_plan_fourier_count(const bri17_rs_plan *plan);
+
+/*
+ * F = (|h|/|N|) iDFT( K^ DFT(u) )   (tests/test_bri17.cpp:56-107)
+ * u_dev, F_dev: [dim][n0_count][N1][(N2)] complex128, distinct buffers; F is
+ * also used as scratch.  Collective; asynchronous on `stream`.
+ */
+BRI17_API int bri17_real_space_apply_f64(bri17_rs_plan *plan, const void *u_dev, void *F_dev,
+                                         void *stream);
+
+/* The two halves, exposed for callers that work in Fourier space:
+ * forward: x_dev (real-space slab, preserved) -> x_hat_dev (Fourier slab
+ *          [dim][N0][k1_count][(N2)]), unnormalised, sign -1 (theory.rst:60);
+ * inverse: x_hat_dev (destroyed) -> x_dev, multiplied by `scale`
+ *          (pass 1/|N| for theory.rst:72). ncomp components (dim or 6, ...). */
+BRI17_API int bri17_rs_forward_fft_f64(bri17_rs_plan *plan, const void *x_dev, void *x_hat_dev,
+                                       int ncomp, void *stream);
+BRI17_API int bri17_rs_inverse_fft_f64(bri17_rs_plan *plan, void *x_hat_dev, void *x_dev,
+                                       int ncomp, double scale, void *stream);
+
+/* The modal plan of the Fourier-side block (k_begin/local_shape helpers). */
+BRI17_API bri17_plan *bri17_rs_plan_modal(bri17_rs_plan *plan);
+
+/* Milliseconds of the phases of the last real-space apply, after a stream
+ * synchronisation: [0] local forward FFT, [1] forward exchange (pack + all-to-
+ * all), [2] axis-0 forward FFT, [3] modal apply, [4] axis-0 inverse FFT,
+ * [5] backward exchange, [6] local inverse FFT, [7] total.  n <= 8. */
+BRI17_API int bri17_rs_plan_last_timings(bri17_rs_plan *plan, double *ms, int n);
+/* Bytes this rank sent to other ranks in one exchange (one direction). */
+BRI17_API int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *plan);
+
+/*
+ * Matrix-free conjugate gradients on  A x = b,  A = the real-space operator
+ * above (symmetric positive semi-definite; null space = constant fields, so b
+ * must have zero mean per component and the solution with zero mean is
+ * returned -- the u^(0) = 0 choice of theory.rst:208-212 / bri17.hpp:336-339).
+ * b_dev, x_dev: real-space slabs (x is overwritten, start from 0).
+ * Stops when |r| <= rtol*|b| or after max_iter iterations; all scalars stay
+ * on the device (no host synchronisation inside an iteration except every
+ * `check_every` iterations for the stopping test).
+ */
+BRI17_API int bri17_cg_solve_f64(bri17_rs_plan *plan, const void *b_dev, void *x_dev, double rtol,
+                                 int max_iter, int check_every, int *iterations,
+                                 double *rel_residual, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRI17_B200_REALSPACE_H */

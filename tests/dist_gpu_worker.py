@@ -1,0 +1,71 @@
+"""torchrun worker (NCCL, one rank per GPU): the distributed real-space
+operator and CG against the numpy restatement, for both exchange modes."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from bri17_b200.realspace import RealSpaceOperator  # noqa: E402
+from oracle import oracle  # noqa: E402
+from realspace_ref import direct_solve_ref, real_space_apply_ref  # noqa: E402
+
+MU, NU = 5.6, 0.3
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    o = oracle.best()
+    ok = True
+    worst = 0.0
+    for mode in (0, 1):
+        for shape in ((9, 7, 5), (16, 12, 10), (12, 10), (32, 32, 32)):
+            dim = len(shape)
+            L = tuple(n * h for n, h in zip(shape, (1.1, 1.2, 1.3)))
+            rng = np.random.default_rng(100 + dim)
+            u = rng.standard_normal((dim,) + shape)
+            u -= u.mean(axis=tuple(range(1, dim + 1)), keepdims=True)
+            ref = real_space_apply_ref(o, shape, L, MU, NU, u + 0j)
+            op = RealSpaceOperator.from_process_group(shape, L, MU, NU, device=local, exchange_mode=mode)
+            a0, a1 = op.n0_begin, op.n0_begin + op.n0_count
+            ud = torch.from_numpy(np.ascontiguousarray(u[:, a0:a1]) + 0j).cuda()
+            for _ in range(2):                       # twice: buffer reuse across applies
+                F = op.apply(ud).cpu().numpy()
+            err = np.abs(F - ref[:, a0:a1]).max() / np.abs(ref).max() if F.size else 0.0
+            # forward transform lands in the axis-1 slab layout
+            xh = op.forward_fft(ud).cpu().numpy()
+            k0, k1 = op.k1_begin, op.k1_begin + op.k1_count
+            href = np.fft.fftn(u, axes=tuple(range(1, dim + 1)))[:, :, k0:k1]
+            err = max(err, np.abs(xh - href).max() / np.abs(href).max() if xh.size else 0.0)
+            back = op.inverse_fft(torch.from_numpy(np.ascontiguousarray(href)).cuda()).cpu().numpy()
+            err = max(err, np.abs(back - u[:, a0:a1]).max() if back.size else 0.0)
+            # CG on b = A u recovers u (zero mean)
+            bd = torch.from_numpy(np.ascontiguousarray(ref[:, a0:a1])).cuda()
+            x, iters, res = op.cg_solve(bd, rtol=1e-11, max_iter=3000, check_every=5)
+            cg_err = np.abs(x.cpu().numpy() - u[:, a0:a1]).max() / np.abs(u).max() if x.numel() else 0.0
+            t = torch.tensor([err, cg_err, res], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            err, cg_err, res = t.tolist()
+            worst = max(worst, err)
+            good = err <= 1e-13 and cg_err <= 1e-7 and res <= 1e-11
+            ok &= good
+            if rank == 0:
+                print(f"mode {mode} shape {shape}: apply/fft err {err:.2e}, cg iters {iters} res {res:.1e} "
+                      f"err {cg_err:.1e} {'ok' if good else 'FAIL'}", flush=True)
+            op.close()
+    if rank == 0:
+        print(("DIST_REALSPACE_OK" if ok else "DIST_REALSPACE_FAIL"), world, f"worst {worst:.2e}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""GPU tests of the end-to-end real-space operator (cuFFT -> modal kernel ->
+cuFFT) and of CG, single GPU; the multi-GPU variants run under torchrun from
+test_multi_gpu_realspace (needs >= 2 GPUs)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from bri17_b200.realspace import RealSpaceOperator  # noqa: E402
+from oracle import kat  # noqa: E402
+from realspace_ref import direct_solve_ref, real_space_apply_ref  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MU, NU = 5.6, 0.3
+
+
+def spacing_L(shape):
+    return tuple(float(n) * h for n, h in zip(shape, (1.1, 1.2, 1.3)))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_kat_end_to_end_on_gpu(dim):
+    """The reference's "Global assembly tests" (tests/test_bri17.cpp:335-361,
+    :363-536) with the WHOLE compute_Ku on the GPU: column j of the dense
+    stiffness matrix = real_space_apply(e_j)."""
+    E = kat.load_elements()
+    shape, L = kat.SHAPE[dim], kat.grid_L(dim)
+    op = RealSpaceOperator(shape, L, kat.MU, kat.NU)
+    size = int(np.prod(shape))
+    K = np.zeros((size * dim, size * dim))
+    u = torch.zeros((dim,) + shape, dtype=torch.complex128, device="cuda")
+    max_imag = 0.0
+    for j in range(size * dim):
+        u.view(-1)[j] = 1.0
+        Ku = op.apply(u).cpu().numpy()
+        u.view(-1)[j] = 0.0
+        max_imag = max(max_imag, float(np.abs(Ku.imag).max()))
+        K[:, j] = Ku.real.ravel()
+    assert max_imag <= kat.IMAG_TOL                                   # :140-144
+    kat.assert_equal(kat.assemble_expected_stiffness(shape, E[f"Ke{dim}"]), K)   # :360, :535
+
+
+@pytest.mark.parametrize("shape", [(16, 12, 10), (64, 64), (5, 7), (8, 8, 33), (32, 32, 32)])
+def test_real_space_apply_vs_numpy_restatement(oracle_mod, shape):
+    dim = len(shape)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(41)
+    u = rng.standard_normal((dim,) + shape) + 0j
+    ref = real_space_apply_ref(oracle_mod.best(), shape, L, MU, NU, u)
+    op = RealSpaceOperator(shape, L, MU, NU)
+    F = op.apply(torch.from_numpy(u).cuda()).cpu().numpy()
+    assert np.abs(F - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(F.imag).max() <= 1e-13 * np.abs(ref).max()
+    t = op.timings()
+    assert t["total"] > 0 and set(t) >= {"modal", "exchange_fwd"}
+
+
+def test_forward_inverse_fft_conventions():
+    """theory.rst:60 (sign -1, unnormalised) and :72 (1/|N| on the inverse)."""
+    shape = (12, 10, 9)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((3,) + shape) + 1j * rng.standard_normal((3,) + shape)
+    op = RealSpaceOperator(shape, spacing_L(shape), MU, NU)
+    xd = torch.from_numpy(x).cuda()
+    xh = op.forward_fft(xd)
+    ref = np.fft.fftn(x, axes=(1, 2, 3))
+    assert np.abs(xh.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert torch.equal(xd.cpu(), torch.from_numpy(x))                 # input preserved
+    back = op.inverse_fft(xh).cpu().numpy()
+    assert np.abs(back - x).max() <= 1e-13 * np.abs(x).max()
+    x6 = rng.standard_normal((6,) + shape) + 0j                        # strain-like field, 6 components
+    xh6 = op.forward_fft(torch.from_numpy(x6).cuda()).cpu().numpy()
+    assert np.abs(xh6 - np.fft.fftn(x6, axes=(1, 2, 3))).max() <= 1e-12
+
+
+@pytest.mark.parametrize("shape", [(16, 12, 10), (24, 20)])
+def test_cg_solves_the_periodic_problem(oracle_mod, shape):
+    dim = len(shape)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(3)
+    x_true = rng.standard_normal((dim,) + shape)
+    x_true -= x_true.mean(axis=tuple(range(1, dim + 1)), keepdims=True)   # u^(0) = 0 (theory.rst:208-212)
+    o = oracle_mod.best()
+    b = real_space_apply_ref(o, shape, L, MU, NU, x_true + 0j)
+    op = RealSpaceOperator(shape, L, MU, NU)
+    x, iters, res = op.cg_solve(torch.from_numpy(b).cuda(), rtol=1e-11, max_iter=2000, check_every=5)
+    x = x.cpu().numpy()
+    assert res <= 1e-11 and 0 < iters < 2000
+    assert np.abs(x - x_true).max() <= 1e-7 * np.abs(x_true).max()
+    direct = direct_solve_ref(o, shape, L, MU, NU, b)
+    assert np.abs(x - direct).max() <= 1e-7 * np.abs(direct).max()
+
+
+def test_multi_gpu_realspace():
+    """World-size-2 run of tests/dist_gpu_worker.py (both exchange modes)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(out.stdout[-3000:], out.stderr[-3000:])
+    assert out.returncode == 0
+    assert f"DIST_REALSPACE_OK {world}" in out.stdout

@@ -28,12 +28,15 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     declared = _declared_symbols()
     assert len(declared) >= 15
-    lib = ctypes.CDLL(_lib.LIB_PATH)
+    core = ctypes.CDLL(_lib.LIB_PATH)
+    rs = ctypes.CDLL(_lib.RS_LIB_PATH)          # needs the core library loaded first
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
-    # and the ctypes table covers the header one to one
-    assert sorted(_lib.SIGNATURES) == declared
+        assert hasattr(core, name) or hasattr(rs, name), \
+            f"{name} declared in include/*.h but not exported"
+    # and the ctypes tables cover the headers one to one
+    assert sorted(list(_lib.SIGNATURES) + list(_lib.RS_SIGNATURES)) == declared
     assert _lib.load().bri17_version() == 100
+    _lib.load_rs()
 
 
 def test_library_is_sm100a_only():
