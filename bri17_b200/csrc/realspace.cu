@@ -68,7 +68,6 @@ struct CopySeg {
   long long src_cs, src_rs, dst_cs, dst_rs;
   int rows;
   int len;
-  long long first_cta;  // prefix sum of CTAs
 };
 struct CopyPlan {
   CopySeg seg[MAX_RANKS];
@@ -76,17 +75,21 @@ struct CopyPlan {
   int ncomp;
   int parts;  // CTAs per row piece
   double scale;
-  long long total_ctas;
+  long long ctas_per_seg;  // grid = nseg * ctas_per_seg, segment index fastest
 };
 
 // Streams contiguous row pieces with 128-bit accesses; the destination may be
-// local HBM or a peer GPU's memory (NVLink stores).  grid = total_ctas.
+// local HBM or a peer GPU's memory (NVLink stores).  Consecutive CTAs belong to
+// DIFFERENT segments (= destination GPUs) and every rank starts its segment
+// list at its right-hand neighbour, so at any instant each GPU spreads its
+// stores over all peers and receives from all peers: an all-to-all that walks
+// the peers in lock step would serialise on one receiver's NVLink ingress.
 __global__ void __launch_bounds__(256) slab_copy_kernel(const CopyPlan cp, int fence_system) {
   const long long cta = blockIdx.x;
-  int s = 0;
-  while (s + 1 < cp.nseg && cta >= cp.seg[s + 1].first_cta) s++;
+  const int s = int(cta % cp.nseg);
   const CopySeg &g = cp.seg[s];
-  long long local = cta - g.first_cta;
+  long long local = cta / cp.nseg;
+  if (local >= (long long)cp.ncomp * g.rows * cp.parts) return;
   const int part = int(local % cp.parts);
   local /= cp.parts;
   const int a = int(local % g.rows);
@@ -223,12 +226,11 @@ struct bri17_rs_plan {
 namespace {
 
 int launch_copy(CopyPlan &cp, int fence, cudaStream_t st) {
-  long long total = 0;
-  for (int s = 0; s < cp.nseg; s++) {
-    cp.seg[s].first_cta = total;
-    total += (long long)cp.ncomp * cp.seg[s].rows * cp.parts;
-  }
-  cp.total_ctas = total;
+  long long per_seg = 0;
+  for (int s = 0; s < cp.nseg; s++)
+    per_seg = std::max(per_seg, (long long)cp.ncomp * cp.seg[s].rows * cp.parts);
+  cp.ctas_per_seg = per_seg;
+  const long long total = per_seg * cp.nseg;
   if (total == 0) return BRI17_OK;
   if (total > 0x7fffffffLL) return fail(BRI17_ERR_UNSUPPORTED, "exchange grid too large");
   slab_copy_kernel<<<(unsigned)total, 256, 0, st>>>(cp, fence);
@@ -263,7 +265,8 @@ int exchange_forward(bri17_rs_plan *p, const double2 *T, double2 *X, double2 *S,
   for (int q = 0; q < P; q++)
     off[q + 1] = off[q] + (long long)ncomp * p->n0_loc * (p->k1_beg[q + 1] - p->k1_beg[q]) * N2e;
   int maxlen = 0;
-  for (int q = 0; q < P; q++) {
+  for (int i = 1; i <= P; i++) {
+    const int q = (r + i) % P;
     const int n1q = p->k1_beg[q + 1] - p->k1_beg[q];
     if (n1q == 0 || p->n0_loc == 0) continue;
     CopySeg &g = cp.seg[cp.nseg++];
@@ -316,7 +319,8 @@ int exchange_backward(bri17_rs_plan *p, const double2 *X, double2 *D, double2 *R
     CopyPlan cp{};
     cp.ncomp = ncomp;
     cp.scale = scale;
-    for (int q = 0; q < P; q++) {
+    for (int i = 1; i <= P; i++) {
+      const int q = (r + i) % P;
       const int n0q = p->n0_beg[q + 1] - p->n0_beg[q];
       if (n0q == 0 || p->n1_loc == 0) continue;
       CopySeg &g = cp.seg[cp.nseg++];

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Timings of the secondary kernels on 512^3 (1 GPU): strain recovery (K3),
+K^/B^ field writers, index map.  CUDA events, 20 launches after 3 warm-ups."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bri17_b200 as b  # noqa: E402
+
+edge = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+shape = (edge,) * 3
+L = tuple(n * h for n, h in zip(shape, (1.1, 1.2, 1.3)))
+op = b.ModalOperator(shape, L, 5.6, 0.3)
+M = edge ** 3
+u = torch.view_as_complex(torch.randn((3,) + shape + (2,), dtype=torch.float64, device="cuda"))
+eps = torch.empty((6,) + shape, dtype=torch.complex128, device="cuda")
+
+
+def timed(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+out = {}
+ms = timed(lambda: op.apply_strain_displacement(u, out=eps))
+out["strain_apply"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * M / ms / 1e6}
+del eps
+slab = (64, edge, edge)      # field writers on a 64-plane slab (144 B/mode output)
+ms = timed(lambda: op.modal_stiffness_field(slab, (100, 0, 0)), 10)
+out["stiffness_field_64planes"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * 64 * edge * edge / ms / 1e6}
+ms = timed(lambda: op.modal_strain_displacement_field(slab, (100, 0, 0)), 10)
+out["strain_field_64planes"] = {"ms": ms, "bytes_per_mode": 48, "gbs": 48 * 64 * edge * edge / ms / 1e6}
+ms = timed(lambda: op.freq_index_map(slab, (100, 0, 0)), 10)
+out["index_map_64planes"] = {"ms": ms, "bytes_per_mode": 12, "gbs": 12 * 64 * edge * edge / ms / 1e6}
+print(json.dumps(out))
