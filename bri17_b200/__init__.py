@@ -134,6 +134,16 @@ class _Hooke:
         _check_contiguous(B, np.dtype(np.complex128), "B")
         check(self._lib.bri17_modal_strain_displacement_mode_f64(self._plan, _p_i32(k), _p_f64(B)))
 
+    def modal_eigenstress_to_opposite_strain(self, k, tau, eta):
+        """Hooke::modal_eigenstress_to_opposite_strain (bri17.hpp:308-355,
+        python/pybri17.cpp:88-95): ``eta`` <- -strain induced by eigenstress ``tau``
+        (Mandel notation, 3 or 6 complex128)."""
+        _check_contiguous(k, np.dtype(np.intc), "k")
+        _check_contiguous(tau, np.dtype(np.complex128), "tau")
+        _check_contiguous(eta, np.dtype(np.complex128), "eta")
+        check(self._lib.bri17_modal_eigenstress_to_opposite_strain_mode_f64(
+            self._plan, _p_i32(k), _p_f64(tau), _p_f64(eta)))
+
     def tables(self, axis):
         """Host copy of the per-axis tables: dict phi/chi/psi/c/s."""
         n = self.grid.shape[axis]
@@ -287,6 +297,49 @@ class ModalOperator:
         check(self._lib.bri17_modal_strain_displacement_field_f64(
             self._plan, _dev_ptr(out), _p_i32(kb), _p_i32(local), _stream_ptr(stream)))
         return out
+
+    # -- per-mode direct solves (bri17.hpp:308-355 batched) ---------------------
+    def _solve(self, fn_name, x, nin, nout, k_begin, mode_major, stream):
+        import torch
+        if x.dtype != torch.complex128:
+            raise ValueError("expected complex128")
+        if mode_major:          # (*local, ncomp): the layout of python/demo.py:21
+            if x.dim() != self.dim + 1 or x.shape[-1] != nin:
+                raise ValueError(f"expected shape (*local, {nin})")
+            local = _ints(x.shape[:-1], self.dim)
+            out = torch.empty(tuple(x.shape[:-1]) + (nout,), dtype=x.dtype, device=x.device)
+            strides = (1, nin, 1, nout)
+        else:
+            kb_, local = self._block(x.shape, nin, k_begin)
+            out = torch.empty((nout,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            strides = (0, 1, 0, 1)
+        kb = _ints(k_begin if k_begin is not None else (0,) * self.dim, self.dim)
+        fn = getattr(self._lib, fn_name)
+        if fn_name == "bri17_eigenstress_to_displacement_f64":
+            rc = fn(self._plan, _dev_ptr(x), _dev_ptr(out), _p_i32(kb), _p_i32(local), *strides,
+                    _stream_ptr(stream))
+        else:
+            rc = fn(self._plan, _dev_ptr(x), _dev_ptr(out), _p_i32(kb), _p_i32(local), strides[0],
+                    strides[1], _stream_ptr(stream))
+        check(rc)
+        return out
+
+    def solve_modal_stiffness(self, f_hat, k_begin=None, mode_major=False, stream=None):
+        """u^ = K^-1 f^ per mode, u^(0) = 0: the exact inverse of apply_modal_stiffness."""
+        return self._solve("bri17_modal_stiffness_solve_f64", f_hat, self.dim, self.dim, k_begin,
+                           mode_major, stream)
+
+    def eigenstress_to_displacement(self, tau_hat, k_begin=None, mode_major=False, stream=None):
+        """u^ = K^-1 (tau^ . conj(B^)) per mode (bri17.hpp:340-341)."""
+        nsym = self.dim * (self.dim + 1) // 2
+        return self._solve("bri17_eigenstress_to_displacement_f64", tau_hat, nsym, self.dim, k_begin,
+                           mode_major, stream)
+
+    def eigenstress_to_opposite_strain(self, tau_hat, k_begin=None, mode_major=False, stream=None):
+        """eta^ = -eps^ induced by the eigenstress tau^ (bri17.hpp:308-355), Mandel notation."""
+        nsym = self.dim * (self.dim + 1) // 2
+        return self._solve("bri17_eigenstress_to_opposite_strain_f64", tau_hat, nsym, nsym, k_begin,
+                           mode_major, stream)
 
     # -- K3 --------------------------------------------------------------------
     def apply_strain_displacement(self, u_hat, out=None, k_begin=None, out_scale=1.0, stream=None):

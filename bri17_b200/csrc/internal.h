@@ -24,9 +24,9 @@ int fail(int code, const std::string &msg);
   } while (0)
 
 // ---- per-axis tables ----------------------------------------------------------
-// Device layout of one axis: five arrays of N doubles, back to back:
-//   phi | chi | psi | c | s        (bri17.hpp:261-263 and :220-221)
-enum { TAB_PHI = 0, TAB_CHI = 1, TAB_PSI = 2, TAB_C = 3, TAB_S = 4, TAB_COUNT = 5 };
+// Device layout of one axis: six arrays of N doubles, back to back:
+//   phi | chi | psi | c | s | alpha   (bri17.hpp:261-263, :220-221 and :218)
+enum { TAB_PHI = 0, TAB_CHI = 1, TAB_PSI = 2, TAB_C = 3, TAB_S = 4, TAB_ALPHA = 5, TAB_COUNT = 6 };
 
 struct AxisTables {
   std::vector<double> host;  // TAB_COUNT * n
@@ -66,6 +66,8 @@ struct ApplyParams {
   double2 *f;
   long long u_stride;   // complex elements between input components
   long long f_stride;   // ... between output components
+  long long u_mstride;  // ... between consecutive modes of the input (1 = planar); solve kernels only
+  long long f_mstride;  // ... of the output
   TileGeom g;
   const double *tab_outer;  // device tables of the slowest axis
   const double *tab_mid;    // middle axis (3-D only)
@@ -124,6 +126,9 @@ int launch_strain_field(bri17_plan *p, const Block &b, void *B, cudaStream_t str
 int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
                         int64_t u_stride, int64_t e_stride, double out_scale,
                         cudaStream_t stream);
+// mode: 0 u^ = K^-1 f^; 1 u^ = K^-1 (tau^ . conj B^); 2 eta^ = sym(B^ (x) u^) of mode 1
+int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, void *out,
+                       int64_t in_cs, int64_t in_ms, int64_t out_cs, int64_t out_ms, cudaStream_t stream);
 int apply_host(bri17_plan *p, const Block &b, const void *u_host, void *f_host,
                int64_t comp_stride, double out_scale);
 void free_host_stages(bri17_plan *p);

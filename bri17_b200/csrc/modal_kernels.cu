@@ -26,6 +26,7 @@
 #include <cstdio>
 
 #include "internal.h"
+#include "mode_math.h"
 
 namespace bri17b200 {
 
@@ -340,32 +341,37 @@ __global__ void __launch_bounds__(256) modal_stiffness_field_kernel(const ApplyP
 // reference's order), the only transcendental evaluated on the GPU.  It is
 // well conditioned (absolute error <= 2 ulp of 1), unlike 1-cos(beta).
 // ---------------------------------------------------------------------------
+// Half-angle factors of one grid line: c = cos(alpha), s = sin(alpha)*N/L, alpha = (pi*k)/N,
+// all three from the host tables (bri17.hpp:218-221).
+struct HalfAngle {
+  double c, s, alpha;
+};
+__device__ __forceinline__ HalfAngle half_angle(const double *tab, int N, int k) {
+  HalfAngle h;
+  h.c = __ldg(tab + size_t(TAB_C) * N + k);
+  h.s = __ldg(tab + size_t(TAB_S) * N + k);
+  h.alpha = __ldg(tab + size_t(TAB_ALPHA) * N + k);
+  return h;
+}
+
+// B^ of one mode from the per-axis factors (bri17.hpp:224-232).
 template <int DIM>
-__device__ __forceinline__ void modal_B(const ApplyParams &p, int ka, int kb, int ki, double2 *B) {
-  constexpr double PI = 3.141592653589793238462643383279502884;
-  const double c0 = __ldg(p.tab_outer + size_t(TAB_C) * p.N_outer + ka);
-  const double s0 = __ldg(p.tab_outer + size_t(TAB_S) * p.N_outer + ka);
-  const double cI = __ldg(p.tab_inner + size_t(TAB_C) * p.N_inner + ki);
-  const double sI = __ldg(p.tab_inner + size_t(TAB_S) * p.N_inner + ki);
-  double sum_alpha = 0.;
-  sum_alpha = add(sum_alpha, __ddiv_rn(mul(PI, double(ka)), double(p.N_outer)));
-  double c1 = 1., s1 = 0.;
-  if constexpr (DIM == 3) {
-    c1 = __ldg(p.tab_mid + size_t(TAB_C) * p.N_mid + kb);
-    s1 = __ldg(p.tab_mid + size_t(TAB_S) * p.N_mid + kb);
-    sum_alpha = add(sum_alpha, __ddiv_rn(mul(PI, double(kb)), double(p.N_mid)));
-  }
-  sum_alpha = add(sum_alpha, __ddiv_rn(mul(PI, double(ki)), double(p.N_inner)));
+__device__ __forceinline__ void modal_B(const HalfAngle &h0, const HalfAngle &h1, const HalfAngle &hI,
+                                        double2 *B) {
+  // sum_alpha accumulates in axis order starting from 0 (:215-219)
+  double sum_alpha = h0.alpha;
+  if constexpr (DIM == 3) sum_alpha = add(sum_alpha, h1.alpha);
+  sum_alpha = add(sum_alpha, hI.alpha);
   double sn, cs;
   sincos(sum_alpha, &sn, &cs);
-  const double pre_re = mul(-2., sn), pre_im = mul(2., cs);
+  const double pre_re = mul(-2., sn), pre_im = mul(2., cs);  // :224
   if constexpr (DIM == 3) {
-    B[0] = make_double2(mul(mul(mul(pre_re, s0), c1), cI), mul(mul(mul(pre_im, s0), c1), cI));
-    B[1] = make_double2(mul(mul(mul(pre_re, c0), s1), cI), mul(mul(mul(pre_im, c0), s1), cI));
-    B[2] = make_double2(mul(mul(mul(pre_re, c0), c1), sI), mul(mul(mul(pre_im, c0), c1), sI));
+    B[0] = make_double2(mul(mul(mul(pre_re, h0.s), h1.c), hI.c), mul(mul(mul(pre_im, h0.s), h1.c), hI.c));
+    B[1] = make_double2(mul(mul(mul(pre_re, h0.c), h1.s), hI.c), mul(mul(mul(pre_im, h0.c), h1.s), hI.c));
+    B[2] = make_double2(mul(mul(mul(pre_re, h0.c), h1.c), hI.s), mul(mul(mul(pre_im, h0.c), h1.c), hI.s));
   } else {
-    B[0] = make_double2(mul(mul(pre_re, s0), cI), mul(mul(pre_im, s0), cI));
-    B[1] = make_double2(mul(mul(pre_re, c0), sI), mul(mul(pre_im, c0), sI));
+    B[0] = make_double2(mul(mul(pre_re, h0.s), hI.c), mul(mul(pre_im, h0.s), hI.c));
+    B[1] = make_double2(mul(mul(pre_re, h0.c), hI.s), mul(mul(pre_im, h0.c), hI.s));
   }
 }
 
@@ -374,28 +380,46 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 
 // MODE 0: write B^ (mode-major).  MODE 1: eps^ = sym(B^ (x) u^), planar Mandel.
+// Same persistent-CTA structure as the stiffness apply: the fastest-axis
+// factors of a thread's columns stay in registers from row to row.
 template <int DIM, int MODE>
-__global__ void __launch_bounds__(256) strain_displacement_kernel(const ApplyParams p) {
+__global__ void __launch_bounds__(256, 2) strain_displacement_kernel(const ApplyParams p) {
   constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
   constexpr int NSYM = DIM * (DIM + 1) / 2;
   const TileGeom &g = p.g;
+  const bool scale_out = p.out_scale != 1.0;
   TileCursor cur;
+  int cached_chunk = -1;
+  int col[VEC];
+  bool ok[VEC];
+  HalfAngle hI[VEC];
   for (cur.init(g); cur.valid(g); cur.next(g)) {
+    if (cur.chunk != cached_chunk) {
+      cached_chunk = cur.chunk;
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        col[j] = cur.chunk * TILE + j * THREADS + threadIdx.x;
+        ok[j] = col[j] < g.n_inner;
+        hI[j] = half_angle(p.tab_inner, p.N_inner, g.kb_inner + (ok[j] ? col[j] : 0));
+      }
+    }
     const long long base = cur.row * g.n_inner;
     double2 u[VEC][DIM];
-    int col[VEC];
+    if constexpr (MODE == 1) {
 #pragma unroll
-    for (int j = 0; j < VEC; j++) {
-      col[j] = cur.chunk * TILE + j * THREADS + threadIdx.x;
-      if (MODE == 1 && col[j] < g.n_inner)
+      for (int j = 0; j < VEC; j++)
 #pragma unroll
-        for (int c = 0; c < DIM; c++) u[j][c] = __ldcs(p.u + c * p.u_stride + base + col[j]);
+        for (int c = 0; c < DIM; c++)
+          if (ok[j]) u[j][c] = __ldcs(p.u + c * p.u_stride + base + col[j]);
     }
+    const HalfAngle h0 = half_angle(p.tab_outer, p.N_outer, g.kb_outer + cur.a);
+    HalfAngle h1 = h0;
+    if constexpr (DIM == 3) h1 = half_angle(p.tab_mid, p.N_mid, g.kb_mid + cur.b);
 #pragma unroll
     for (int j = 0; j < VEC; j++) {
-      if (col[j] >= g.n_inner) continue;
+      if (!ok[j]) continue;
       double2 B[DIM];
-      modal_B<DIM>(p, g.kb_outer + cur.a, g.kb_mid + cur.b, g.kb_inner + col[j], B);
+      modal_B<DIM>(h0, h1, hI[j], B);
       if constexpr (MODE == 0) {
         double2 *o = p.f + (base + col[j]) * DIM;
 #pragma unroll
@@ -404,20 +428,121 @@ __global__ void __launch_bounds__(256) strain_displacement_kernel(const ApplyPar
         // Mandel order: tests/test_bri17.cpp:207-209 (2-D), :224-230 (3-D)
         constexpr int P3[6] = {0, 1, 2, 1, 2, 0}, Q3[6] = {0, 1, 2, 2, 0, 1};
         constexpr int P2[3] = {0, 1, 0}, Q2[3] = {0, 1, 1};
-        const double sqrt2 = 1.4142135623730951;  // sqrt(2) rounded to double
+        // sqrt(2)*(0.5*x) == (sqrt(2)/2)*x bit for bit: halving is exact
+        const double half_sqrt2 = 0.5 * 1.4142135623730951;
         double2 *o = p.f + base + col[j];
 #pragma unroll
         for (int s = 0; s < NSYM; s++) {
           const int pp = DIM == 3 ? P3[s] : P2[s], qq = DIM == 3 ? Q3[s] : Q2[s];
-          const double2 t1 = cmul(B[pp], u[j][qq]);  // :206, :223
-          const double2 t2 = cmul(u[j][pp], B[qq]);
-          double2 e = make_double2(mul(0.5, add(t1.x, t2.x)), mul(0.5, add(t1.y, t2.y)));
-          if (pp != qq) e = make_double2(mul(sqrt2, e.x), mul(sqrt2, e.y));
-          if (p.out_scale != 1.0) e = make_double2(mul(e.x, p.out_scale), mul(e.y, p.out_scale));
+          double2 e;
+          if (pp == qq) {
+            // 0.5*(B_p u_p + u_p B_p): both products are bit-identical, so the sum is an
+            // exact doubling and the half undoes it exactly (:206, :223)
+            e = cmul(B[pp], u[j][pp]);
+          } else {
+            const double2 t1 = cmul(B[pp], u[j][qq]);
+            const double2 t2 = cmul(u[j][pp], B[qq]);
+            e = make_double2(mul(half_sqrt2, add(t1.x, t2.x)), mul(half_sqrt2, add(t1.y, t2.y)));
+          }
+          if (scale_out) e = make_double2(mul(e.x, p.out_scale), mul(e.y, p.out_scale));
           __stcs(o + s * p.f_stride, e);
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-mode direct solves (bri17.hpp:308-355).
+//   MODE 0: u^ = K^-1 f^                      (exact inverse of the stiffness apply, u^(0) = 0)
+//   MODE 1: u^ = K^-1 (tau^ . conj(B^))        (bri17.hpp:324-341)
+//   MODE 2: eta^ = sym(B^ (x) u^), u^ of MODE 1 (bri17.hpp:342-353): -strain induced by an eigenstress
+// K^ and B^ are rebuilt per mode from the tables; the 2x2/3x3 Cholesky runs in registers.
+// Input/output element (s, i) at base[i*mstride + s*cstride]: planar (mstride 1) or
+// mode-major (cstride 1), the layout of python/demo.py:21,37-38.
+// ---------------------------------------------------------------------------
+struct AxisFactors {
+  double phi, chi, psi, c, s, alpha;
+};
+__device__ __forceinline__ AxisFactors axis_factors(const double *tab, int N, int k) {
+  AxisFactors f;
+  f.phi = __ldg(tab + size_t(TAB_PHI) * N + k);
+  f.chi = __ldg(tab + size_t(TAB_CHI) * N + k);
+  f.psi = __ldg(tab + size_t(TAB_PSI) * N + k);
+  f.c = __ldg(tab + size_t(TAB_C) * N + k);
+  f.s = __ldg(tab + size_t(TAB_S) * N + k);
+  f.alpha = __ldg(tab + size_t(TAB_ALPHA) * N + k);
+  return f;
+}
+
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(256, 2) modal_solve_kernel(const ApplyParams p) {
+  constexpr int THREADS = 256, TILE = THREADS;
+  constexpr int NIN = MODE == 0 ? DIM : DIM * (DIM + 1) / 2;
+  constexpr int NOUT = MODE == 2 ? DIM * (DIM + 1) / 2 : DIM;
+  const TileGeom &g = p.g;
+  TileCursor cur;
+  int cached_chunk = -1, col = 0;
+  bool ok = false;
+  AxisFactors fI{};
+  for (cur.init(g); cur.valid(g); cur.next(g)) {
+    if (cur.chunk != cached_chunk) {
+      cached_chunk = cur.chunk;
+      col = cur.chunk * TILE + threadIdx.x;
+      ok = col < g.n_inner;
+      fI = axis_factors(p.tab_inner, p.N_inner, g.kb_inner + (ok ? col : 0));
+    }
+    if (!ok) continue;
+    const long long i = cur.row * g.n_inner + col;
+    Cplx in[NIN];
+#pragma unroll
+    for (int s = 0; s < NIN; s++) {
+      const double2 v = __ldcs(p.u + i * p.u_mstride + s * p.u_stride);
+      in[s] = {v.x, v.y};
+    }
+    const int k0 = g.kb_outer + cur.a, k1 = g.kb_mid + cur.b, kI = g.kb_inner + col;
+    const AxisFactors f0 = axis_factors(p.tab_outer, p.N_outer, k0);
+    AxisFactors f1 = f0;
+    if constexpr (DIM == 3) f1 = axis_factors(p.tab_mid, p.N_mid, k1);
+    Cplx out[NOUT];
+    const bool null_frequency = (k0 == 0) && (DIM == 2 || k1 == 0) && (kI == 0);   // bri17.hpp:327,334
+    if (null_frequency) {
+#pragma unroll
+      for (int s = 0; s < NOUT; s++) out[s] = {0., 0.};                            // :336-339
+    } else {
+      double phi[DIM], chi[DIM], psi[DIM], c[DIM], sh[DIM];
+      phi[0] = f0.phi; chi[0] = f0.chi; psi[0] = f0.psi; c[0] = f0.c; sh[0] = f0.s;
+      if constexpr (DIM == 3) { phi[1] = f1.phi; chi[1] = f1.chi; psi[1] = f1.psi; c[1] = f1.c; sh[1] = f1.s; }
+      phi[DIM - 1] = fI.phi; chi[DIM - 1] = fI.chi; psi[DIM - 1] = fI.psi; c[DIM - 1] = fI.c; sh[DIM - 1] = fI.s;
+      double K[DIM][DIM];
+      stiffness_entries<DIM>(phi, chi, psi, p.mu, p.scaling, K);
+      Cplx u[DIM];
+      if constexpr (MODE == 0) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) u[d] = in[d];
+        cholesky_solve<DIM>(K, u);
+#pragma unroll
+        for (int d = 0; d < DIM; d++) out[d] = u[d];
+      } else {
+        double sum_alpha = f0.alpha;
+        if constexpr (DIM == 3) sum_alpha = sum_alpha + f1.alpha;
+        sum_alpha = sum_alpha + fI.alpha;
+        double sn, cs;
+        sincos(sum_alpha, &sn, &cs);
+        Cplx B[DIM];
+        strain_displacement_entries<DIM>(c, sh, Cplx{-2. * sn, 2. * cs}, B);
+        eigenstress_to_displacement<DIM>(in, B, K, u);
+        if constexpr (MODE == 1) {
+#pragma unroll
+          for (int d = 0; d < DIM; d++) out[d] = u[d];
+        } else {
+          displacement_to_strain<DIM>(B, u, out);
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NOUT; s++)
+      __stcs(p.f + i * p.f_mstride + s * p.f_stride, make_double2(out[s].re, out[s].im));
   }
 }
 
@@ -511,6 +636,7 @@ static void fill_params(const bri17_plan *p, const Block &b, ApplyParams *ap) {
   ap->u = nullptr;
   ap->f = nullptr;
   ap->u_stride = ap->f_stride = 0;
+  ap->u_mstride = ap->f_mstride = 1;
 }
 
 static int check_launch(const char *what) {
@@ -575,7 +701,7 @@ int launch_strain_field(bri17_plan *p, const Block &b, void *B, cudaStream_t str
   ApplyParams ap;
   fill_params(p, b, &ap);
   ap.f = static_cast<double2 *>(B);
-  const int grid = make_geom(b, 512, p->sm_count * 4, &ap.g);
+  const int grid = make_geom(b, 512, p->sm_count * 2, &ap.g);
   if (b.dim == 3) strain_displacement_kernel<3, 0><<<grid, 256, 0, stream>>>(ap);
   else strain_displacement_kernel<2, 0><<<grid, 256, 0, stream>>>(ap);
   p->launches++;
@@ -592,11 +718,33 @@ int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
   ap.u_stride = u_stride;
   ap.f_stride = e_stride;
   ap.out_scale = out_scale;
-  const int grid = make_geom(b, 512, p->sm_count * 4, &ap.g);
+  const int grid = make_geom(b, 512, p->sm_count * 2, &ap.g);
   if (b.dim == 3) strain_displacement_kernel<3, 1><<<grid, 256, 0, stream>>>(ap);
   else strain_displacement_kernel<2, 1><<<grid, 256, 0, stream>>>(ap);
   p->launches++;
   return check_launch("strain_displacement_apply");
+}
+
+int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, void *out,
+                       int64_t in_cs, int64_t in_ms, int64_t out_cs, int64_t out_ms, cudaStream_t stream) {
+  ApplyParams ap;
+  fill_params(p, b, &ap);
+  ap.u = static_cast<const double2 *>(in);
+  ap.f = static_cast<double2 *>(out);
+  ap.u_stride = in_cs; ap.u_mstride = in_ms;
+  ap.f_stride = out_cs; ap.f_mstride = out_ms;
+  const int grid = make_geom(b, 256, p->sm_count * 2, &ap.g);
+  if (b.dim == 3) {
+    if (mode == 0) modal_solve_kernel<3, 0><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 1) modal_solve_kernel<3, 1><<<grid, 256, 0, stream>>>(ap);
+    else modal_solve_kernel<3, 2><<<grid, 256, 0, stream>>>(ap);
+  } else {
+    if (mode == 0) modal_solve_kernel<2, 0><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 1) modal_solve_kernel<2, 1><<<grid, 256, 0, stream>>>(ap);
+    else modal_solve_kernel<2, 2><<<grid, 256, 0, stream>>>(ap);
+  }
+  p->launches++;
+  return check_launch("modal_solve");
 }
 
 }  // namespace bri17b200

@@ -12,6 +12,7 @@
 #include <numbers>
 
 #include "internal.h"
+#include "mode_math.h"
 
 namespace bri17b200 {
 
@@ -32,6 +33,7 @@ static void fill_axis_tables(AxisTables &t, int n, double L) {
   double *psi = t.host.data() + size_t(TAB_PSI) * n;
   double *c = t.host.data() + size_t(TAB_C) * n;
   double *s = t.host.data() + size_t(TAB_S) * n;
+  double *al = t.host.data() + size_t(TAB_ALPHA) * n;
   for (int k = 0; k < n; k++) {
     const double h = L / n;                                   // :259
     const double beta = 2 * std::numbers::pi_v<double> * k / n;  // :260
@@ -41,6 +43,7 @@ static void fill_axis_tables(AxisTables &t, int n, double L) {
     const double alpha = std::numbers::pi_v<double> * k / n;  // :218
     c[k] = std::cos(alpha);                                   // :220
     s[k] = std::sin(alpha) * n / L;                           // :221
+    al[k] = alpha;                                            // summed per mode on the device (:219)
   }
 }
 
@@ -211,8 +214,8 @@ int bri17_plan_get_tables(const bri17_plan *p, int axis, double *phi, double *ch
                           double *psi, double *c, double *s) {
   if (!p || axis < 0 || axis >= p->dim) return fail(BRI17_ERR_INVALID_ARG, "bad plan/axis");
   const AxisTables &t = p->tab[axis];
-  double *outs[TAB_COUNT] = {phi, chi, psi, c, s};
-  for (int w = 0; w < TAB_COUNT; w++)
+  double *outs[5] = {phi, chi, psi, c, s};
+  for (int w = 0; w < 5; w++)
     if (outs[w]) std::memcpy(outs[w], t.h(w), sizeof(double) * t.n);
   return BRI17_OK;
 }
@@ -281,6 +284,87 @@ int bri17_modal_strain_displacement_mode_f64(const bri17_plan *p, const int *k, 
     }
   }
   return BRI17_OK;
+}
+
+// Hooke::modal_eigenstress_to_opposite_strain, bri17.hpp:308-355, one mode on the host.
+int bri17_modal_eigenstress_to_opposite_strain_mode_f64(const bri17_plan *p, const int *k,
+                                                        const double *tau, double *eta) {
+  if (!p || !k || !tau || !eta) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  const int dim = p->dim, nsym = dim * (dim + 1) / 2;
+  double phi[3], chi[3], psi[3], c[3], s[3];
+  double sum_alpha = 0.;
+  bool null_frequency = true;
+  for (int d = 0; d < dim; d++) {
+    if (k[d] < 0 || k[d] >= p->shape[d])
+      return fail(BRI17_ERR_INVALID_ARG, "frequency index outside [0, shape)");
+    null_frequency = null_frequency && k[d] == 0;
+    phi[d] = p->tab[d].h(TAB_PHI)[k[d]]; chi[d] = p->tab[d].h(TAB_CHI)[k[d]];
+    psi[d] = p->tab[d].h(TAB_PSI)[k[d]];
+    c[d] = p->tab[d].h(TAB_C)[k[d]]; s[d] = p->tab[d].h(TAB_S)[k[d]];
+    sum_alpha += p->tab[d].h(TAB_ALPHA)[k[d]];
+  }
+  if (null_frequency) {  // :336-339
+    for (int i = 0; i < 2 * nsym; i++) eta[i] = 0.;
+    return BRI17_OK;
+  }
+  const Cplx pre{-2 * std::sin(sum_alpha), 2 * std::cos(sum_alpha)};
+  Cplx t[6], e[6];
+  for (int i = 0; i < nsym; i++) t[i] = {tau[2 * i], tau[2 * i + 1]};
+  if (dim == 2) {
+    double K[2][2];
+    Cplx B[2], u[2];
+    stiffness_entries<2>(phi, chi, psi, p->mu, p->scaling, K);
+    strain_displacement_entries<2>(c, s, pre, B);
+    eigenstress_to_displacement<2>(t, B, K, u);
+    displacement_to_strain<2>(B, u, e);
+  } else {
+    double K[3][3];
+    Cplx B[3], u[3];
+    stiffness_entries<3>(phi, chi, psi, p->mu, p->scaling, K);
+    strain_displacement_entries<3>(c, s, pre, B);
+    eigenstress_to_displacement<3>(t, B, K, u);
+    displacement_to_strain<3>(B, u, e);
+  }
+  for (int i = 0; i < nsym; i++) { eta[2 * i] = e[i].re; eta[2 * i + 1] = e[i].im; }
+  return BRI17_OK;
+}
+
+static int solve_entry(bri17_plan *p, int mode, const void *in, void *out, const int *k_begin,
+                       const int *local_shape, int64_t in_cs, int64_t in_ms, int64_t out_cs,
+                       int64_t out_ms, void *stream) {
+  if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");
+  Block b;
+  int rc = make_block(p, k_begin, local_shape, &b);
+  if (rc) return rc;
+  if (b.modes == 0) return BRI17_OK;
+  if ((rc = check_dev_ptr(in, "input field")) || (rc = check_dev_ptr(out, "output field"))) return rc;
+  if (in_ms == 0) in_ms = 1;
+  if (out_ms == 0) out_ms = 1;
+  if (in_cs == 0) in_cs = in_ms == 1 ? b.modes : 1;
+  if (out_cs == 0) out_cs = out_ms == 1 ? b.modes : 1;
+  if (in_cs < 1 || in_ms < 1 || out_cs < 1 || out_ms < 1)
+    return fail(BRI17_ERR_INVALID_ARG, "strides must be positive");
+  return on_device(p, [&] {
+    return launch_modal_solve(p, b, mode, in, out, in_cs, in_ms, out_cs, out_ms, cudaStream_t(stream));
+  });
+}
+
+int bri17_modal_stiffness_solve_f64(bri17_plan *p, const void *f, void *u, const int *k_begin,
+                                    const int *local_shape, int64_t comp_stride, int64_t mode_stride,
+                                    void *stream) {
+  return solve_entry(p, 0, f, u, k_begin, local_shape, comp_stride, mode_stride, comp_stride, mode_stride, stream);
+}
+
+int bri17_eigenstress_to_displacement_f64(bri17_plan *p, const void *tau, void *u, const int *k_begin,
+                                          const int *local_shape, int64_t tau_cs, int64_t tau_ms,
+                                          int64_t u_cs, int64_t u_ms, void *stream) {
+  return solve_entry(p, 1, tau, u, k_begin, local_shape, tau_cs, tau_ms, u_cs, u_ms, stream);
+}
+
+int bri17_eigenstress_to_opposite_strain_f64(bri17_plan *p, const void *tau, void *eta, const int *k_begin,
+                                             const int *local_shape, int64_t comp_stride,
+                                             int64_t mode_stride, void *stream) {
+  return solve_entry(p, 2, tau, eta, k_begin, local_shape, comp_stride, mode_stride, comp_stride, mode_stride, stream);
 }
 
 int bri17_modal_stiffness_apply_f64(bri17_plan *p, const void *u, void *f, const int *k_begin,

@@ -105,6 +105,13 @@ BRI17_API int bri17_modal_stiffness_mode_f64(const bri17_plan *plan, const int *
 /* Hooke::modal_strain_displacement (bri17.hpp:212-236): B[dim] interleaved. */
 BRI17_API int bri17_modal_strain_displacement_mode_f64(const bri17_plan *plan, const int *k, double *B);
 
+/* Hooke::modal_eigenstress_to_opposite_strain (bri17.hpp:308-355): tau[nsym] ->
+ * eta[nsym], Mandel notation (nsym = 3 in 2-D, 6 in 3-D), zero at k = 0.  The
+ * reference solves K^ u = tau.conj(B^) with Eigen's LLT; this build uses its own
+ * Cholesky (no reference test pins the result: parity unpinned). */
+BRI17_API int bri17_modal_eigenstress_to_opposite_strain_mode_f64(const bri17_plan *plan, const int *k,
+                                                                  const double *tau, double *eta);
+
 /* ---- every frequency of a block, device side ----------------------------- */
 
 /*
@@ -153,6 +160,30 @@ BRI17_API int bri17_strain_displacement_apply_f64(bri17_plan *plan, const void *
                                         void *eps_hat_dev, const int *k_begin,
                                         const int *local_shape, int64_t u_stride,
                                         int64_t eps_stride, double out_scale, void *stream);
+
+/*
+ * Per-mode direct solves, every mode of the block (bri17.hpp:308-355 batched;
+ * the reference drives them from a Python double loop, python/demo.py:33-40).
+ * Element (s, i) of a field lives at base[i*mode_stride + s*comp_stride]:
+ *   planar      mode_stride = 1, comp_stride >= modes   (0, 0 selects this)
+ *   mode-major  mode_stride = ncomp, comp_stride = 1     (python/demo.py:21,37-38)
+ *
+ * bri17_modal_stiffness_solve_f64:           u^ = K^-1 f^, u^(0) = 0 (theory.rst:208-212); dim -> dim
+ * bri17_eigenstress_to_displacement_f64:     u^ = K^-1 (tau^ . conj(B^))  (bri17.hpp:340-341); nsym -> dim
+ * bri17_eigenstress_to_opposite_strain_f64:  eta^ = sym(B^ (x) u^), Mandel (bri17.hpp:342-353); nsym -> nsym
+ */
+BRI17_API int bri17_modal_stiffness_solve_f64(bri17_plan *plan, const void *f_hat_dev, void *u_hat_dev,
+                                              const int *k_begin, const int *local_shape,
+                                              int64_t comp_stride, int64_t mode_stride, void *stream);
+BRI17_API int bri17_eigenstress_to_displacement_f64(bri17_plan *plan, const void *tau_hat_dev,
+                                                    void *u_hat_dev, const int *k_begin,
+                                                    const int *local_shape, int64_t tau_comp_stride,
+                                                    int64_t tau_mode_stride, int64_t u_comp_stride,
+                                                    int64_t u_mode_stride, void *stream);
+BRI17_API int bri17_eigenstress_to_opposite_strain_f64(bri17_plan *plan, const void *tau_hat_dev,
+                                                       void *eta_hat_dev, const int *k_begin,
+                                                       const int *local_shape, int64_t comp_stride,
+                                                       int64_t mode_stride, void *stream);
 
 /* Frequency multi-index the kernels derive for every linear element of the
  * block: k_out_dev[i*dim + d] (int32).  Uses the same tile cursor as the apply

@@ -13,7 +13,8 @@
  * the reference header compiled for baseline x86-64 (no FMA), which is what
  * tests/test_oracle_vs_ref.py checks against oracle/_ref/libbri17_ref.so.
  *
- * Parity status: PINNED.  (1) bit-for-bit against the unmodified reference
+ * Parity status: PINNED for the hot path (UNPINNED only for
+ * oracle_modal_eigenstress_to_opposite_strain, see its comment).  (1) bit-for-bit against the unmodified reference
  * header compiled in oracle/_ref (modal_stiffness, modal_strain_displacement,
  * whole-grid apply); (2) against the reference's own known-answer tests --
  * the Maxima-derived element matrices of tests/test_bri17.cpp:344-356,
@@ -260,6 +261,118 @@ void oracle_apply_strain_displacement(int dim, const int *shape,
           eps_hat[2 * (i + s * e_stride)] = er;
           eps_hat[2 * (i + s * e_stride) + 1] = ei;
         }
+      }
+}
+
+/*
+ * Hooke<double,DIM>::modal_eigenstress_to_opposite_strain -- bri17.hpp:308-355.
+ * tau, eta: nsym complex numbers (Mandel notation), interleaved.
+ *
+ * PARITY UNPINNED: the reference solves K u = rhs with Eigen's K.llt().solve()
+ * (:341); Eigen is neither vendored nor installed and no reference test calls
+ * this method (only python/demo.py does).  The LLT solve is restated as the
+ * textbook Cholesky factorisation K = L L^T (column by column, L real because
+ * Im K = 0) followed by forward and backward substitution.
+ * out_u (may be NULL) receives the intermediate displacement u (DIM complex).
+ */
+void oracle_modal_eigenstress_to_opposite_strain(int dim, const int *shape, const double *L,
+                                                 double mu, double nu, const int *k,
+                                                 const double *tau, double *eta, double *out_u) {
+  const int nsym = dim == 2 ? 3 : 6;                       /* :315 */
+  const double sqrt2 = 1.4142135623730951;                 /* :313 */
+  double Bf[6], Kf[18];
+  oracle_modal_strain_displacement(dim, shape, L, k, Bf);  /* :317 */
+  oracle_modal_stiffness(dim, shape, L, mu, nu, k, Kf);    /* :319 */
+  int null_frequency = 1;                                  /* :327, :334 */
+  for (int d = 0; d < dim; d++) null_frequency = null_frequency && (k[d] == 0);
+  if (null_frequency) {                                    /* :336-339 */
+    for (int i = 0; i < 2 * nsym; i++) eta[i] = 0.;
+    if (out_u) for (int i = 0; i < 2 * dim; i++) out_u[i] = 0.;
+    return;
+  }
+  /* tau_mat, :324-325 (2-D), :330-332 (3-D) */
+  double tr[3][3], ti[3][3];
+  const int p2[3][2] = {{0, 0}, {1, 1}, {0, 1}};
+  const int p3[6][2] = {{0, 0}, {1, 1}, {2, 2}, {1, 2}, {2, 0}, {0, 1}};
+  for (int s = 0; s < nsym; s++) {
+    int p = dim == 2 ? p2[s][0] : p3[s][0], q = dim == 2 ? p2[s][1] : p3[s][1];
+    if (p == q) { tr[p][p] = tau[2 * s]; ti[p][p] = tau[2 * s + 1]; }
+    else {
+      tr[p][q] = tr[q][p] = tau[2 * s] / sqrt2;
+      ti[p][q] = ti[q][p] = tau[2 * s + 1] / sqrt2;
+    }
+  }
+  /* rhs = tau_mat * conj(B), :340 */
+  double ur[3], ui[3];
+  for (int i = 0; i < dim; i++) {
+    double accr = 0., acci = 0.;
+    for (int j = 0; j < dim; j++) {
+      double br = Bf[2 * j], bi = -Bf[2 * j + 1];
+      double pr = tr[i][j] * br - ti[i][j] * bi;
+      double pi = tr[i][j] * bi + ti[i][j] * br;
+      if (j == 0) { accr = pr; acci = pi; } else { accr = accr + pr; acci = acci + pi; }
+    }
+    ur[i] = accr; ui[i] = acci;
+  }
+  /* u = K.llt().solve(rhs), :341 */
+  double A[3][3];
+  for (int i = 0; i < dim; i++)
+    for (int j = 0; j < dim; j++) A[i][j] = Kf[2 * (dim * i + j)];
+  for (int j = 0; j < dim; j++) {
+    double d = A[j][j];
+    for (int p = 0; p < j; p++) d -= A[j][p] * A[j][p];
+    d = sqrt(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < dim; i++) {
+      double t = A[i][j];
+      for (int p = 0; p < j; p++) t -= A[i][p] * A[j][p];
+      A[i][j] = t / d;
+    }
+  }
+  for (int i = 0; i < dim; i++) {
+    double sr = ur[i], si = ui[i];
+    for (int p = 0; p < i; p++) { sr -= A[i][p] * ur[p]; si -= A[i][p] * ui[p]; }
+    ur[i] = sr / A[i][i]; ui[i] = si / A[i][i];
+  }
+  for (int i = dim - 1; i >= 0; i--) {
+    double sr = ur[i], si = ui[i];
+    for (int p = i + 1; p < dim; p++) { sr -= A[p][i] * ur[p]; si -= A[p][i] * ui[p]; }
+    ur[i] = sr / A[i][i]; ui[i] = si / A[i][i];
+  }
+  if (out_u) for (int i = 0; i < dim; i++) { out_u[2 * i] = ur[i]; out_u[2 * i + 1] = ui[i]; }
+  /* eta_mat = 0.5 (B u^T + u B^T), :342; Mandel with sqrt2 on shear, :344-353 */
+  for (int s = 0; s < nsym; s++) {
+    int p = dim == 2 ? p2[s][0] : p3[s][0], q = dim == 2 ? p2[s][1] : p3[s][1];
+    double t1r, t1i, t2r, t2i;
+    cmul(Bf[2 * p], Bf[2 * p + 1], ur[q], ui[q], &t1r, &t1i);
+    cmul(ur[p], ui[p], Bf[2 * q], Bf[2 * q + 1], &t2r, &t2i);
+    double er = 0.5 * (t1r + t2r), ei = 0.5 * (t1i + t2i);
+    if (p != q) { er = sqrt2 * er; ei = sqrt2 * ei; }
+    eta[2 * s] = er; eta[2 * s + 1] = ei;
+  }
+}
+
+/*
+ * The per-mode loop of python/demo.py:33-40 over a row-major block, planar
+ * fields: eta^ (nsym comps) and u^ (dim comps) from tau^ (nsym comps).  Either
+ * output may be NULL.
+ */
+void oracle_apply_eigenstress(int dim, const int *shape, const double *L, double mu, double nu,
+                              const int *k_begin, const int *local_shape, const double *tau_hat,
+                              double *eta_hat, double *u_hat) {
+  const int n0 = local_shape[0], n1 = local_shape[1], n2 = dim == 3 ? local_shape[2] : 1;
+  const int nsym = dim == 2 ? 3 : 6;
+  const int64_t M = (int64_t)n0 * n1 * n2;
+  for (int a = 0; a < n0; a++)
+    for (int b = 0; b < n1; b++)
+      for (int c = 0; c < n2; c++) {
+        int k[3] = {k_begin[0] + a, k_begin[1] + b, dim == 3 ? k_begin[2] + c : 0};
+        int64_t i = ((int64_t)a * n1 + b) * n2 + c;
+        double tau[12], eta[12], u[6];
+        for (int s = 0; s < nsym; s++) { tau[2 * s] = tau_hat[2 * (i + s * M)]; tau[2 * s + 1] = tau_hat[2 * (i + s * M) + 1]; }
+        oracle_modal_eigenstress_to_opposite_strain(dim, shape, L, mu, nu, k, tau, eta, u);
+        if (eta_hat) for (int s = 0; s < nsym; s++) { eta_hat[2 * (i + s * M)] = eta[2 * s]; eta_hat[2 * (i + s * M) + 1] = eta[2 * s + 1]; }
+        if (u_hat) for (int s = 0; s < dim; s++) { u_hat[2 * (i + s * M)] = u[2 * s]; u_hat[2 * (i + s * M) + 1] = u[2 * s + 1]; }
       }
 }
 

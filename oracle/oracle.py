@@ -162,6 +162,29 @@ def best(fast: bool = False) -> _Impl:
     return ref(fast) or port(fast)
 
 
+def apply_eigenstress(shape, L, mu, nu, tau_hat, k_begin=None):
+    """Per-mode eigenstress solve over a block (python/demo.py:33-40 loop, C port
+    only -- the compiled reference cannot instantiate the Eigen-based method):
+    returns (eta_hat[nsym, *local], u_hat[dim, *local]).  PARITY UNPINNED."""
+    lib = port().lib
+    dim = len(shape)
+    nsym = dim * (dim + 1) // 2
+    tau_hat = np.ascontiguousarray(tau_hat, dtype=np.complex128)
+    local = tau_hat.shape[1:]
+    assert tau_hat.shape[0] == nsym
+    if k_begin is None:
+        k_begin = (0,) * dim
+    eta = np.empty_like(tau_hat)
+    u = np.empty((dim,) + tuple(local), dtype=np.complex128)
+    _, sp = _ints(shape); _, lp = _dbls(L); _, kb = _ints(k_begin); _, ls = _ints(local)
+    lib.oracle_apply_eigenstress.argtypes = [C.c_int, _i32p, _f64p, C.c_double, C.c_double, _i32p, _i32p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_apply_eigenstress.restype = None
+    lib.oracle_apply_eigenstress(dim, sp, lp, mu, nu, kb, ls, tau_hat.ctypes.data, eta.ctypes.data,
+                                 u.ctypes.data)
+    return eta, u
+
+
 def freq_index_map(k_begin, local_shape) -> np.ndarray:
     """Multi-index of every linear element of a row-major block
     (tests/test_bri17.cpp:62-64,71 / :76-79,88), int32 ``[prod(local), dim]``."""

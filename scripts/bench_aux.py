@@ -36,6 +36,14 @@ out = {}
 ms = timed(lambda: op.apply_strain_displacement(u, out=eps))
 out["strain_apply"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * M / ms / 1e6}
 del eps
+tau = torch.view_as_complex(torch.randn((6,) + shape + (2,), dtype=torch.float64, device="cuda"))
+ms = timed(lambda: op.eigenstress_to_opposite_strain(tau), 10)
+out["eigenstress_to_opposite_strain"] = {"ms": ms, "bytes_per_mode": 192, "gbs": 192 * M / ms / 1e6}
+ms = timed(lambda: op.eigenstress_to_displacement(tau), 10)
+out["eigenstress_to_displacement"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * M / ms / 1e6}
+del tau
+ms = timed(lambda: op.solve_modal_stiffness(u), 10)
+out["modal_stiffness_solve"] = {"ms": ms, "bytes_per_mode": 96, "gbs": 96 * M / ms / 1e6}
 slab = (64, edge, edge)      # field writers on a 64-plane slab (144 B/mode output)
 ms = timed(lambda: op.modal_stiffness_field(slab, (100, 0, 0)), 10)
 out["stiffness_field_64planes"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * 64 * edge * edge / ms / 1e6}

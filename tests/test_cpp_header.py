@@ -81,13 +81,17 @@ def test_eigenstress_to_opposite_strain(oracle_mod, hdr, dim):
     ll = np.array(L, dtype=np.float64)
     s2 = np.sqrt(2.0)
     pairs = [(0, 0), (1, 1), (0, 1)] if dim == 2 else [(0, 0), (1, 1), (2, 2), (1, 2), (2, 0), (0, 1)]
+    tau_all = rng.standard_normal((nsym,) + shape) + 1j * rng.standard_normal((nsym,) + shape)
+    eta_oracle, _ = oracle_mod.apply_eigenstress(shape, L, 1.0, 0.3, tau_all)
     for k in list(np.ndindex(*shape))[::3]:
-        tau = rng.standard_normal(nsym) + 1j * rng.standard_normal(nsym)
+        tau = np.ascontiguousarray(tau_all[(slice(None),) + k])
         eta = np.empty(nsym, dtype=np.complex128)
         kk = np.array(k, dtype=np.intc)
         hdr.lib.hdr_eigenstress_to_opposite_strain(dim, sh.ctypes.data_as(i32p), ll.ctypes.data_as(f64p),
                                                    1.0, 0.3, kk.ctypes.data_as(i32p),
                                                    tau.ctypes.data_as(f64p), eta.ctypes.data_as(f64p))
+        # same Cholesky, same order: header == oracle restatement bit for bit
+        assert np.array_equal(eta, eta_oracle[(slice(None),) + k])
         if not any(k):
             assert np.all(eta == 0)
             continue
