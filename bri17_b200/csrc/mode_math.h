@@ -140,7 +140,6 @@ BRI17_HD void mandel_pair(int s, int &p, int &q) {
 template <int DIM>
 BRI17_HD void eigenstress_to_displacement(const Cplx *tau, const Cplx (&B)[DIM], double (&K)[DIM][DIM],
                                           Cplx (&u)[DIM]) {
-  const double sqrt2 = 1.4142135623730951;  // std::numbers::sqrt2_v<double>
   Cplx t[DIM][DIM];
   for (int s = 0; s < Mandel<DIM>::nsym; s++) {
     int p, q;
@@ -150,7 +149,7 @@ BRI17_HD void eigenstress_to_displacement(const Cplx *tau, const Cplx (&B)[DIM],
 #ifdef __CUDA_ARCH__
       t[p][q] = t[q][p] = cscale(0.7071067811865476, tau[s]);  // 1/sqrt2: avoids two fp64 divides per entry
 #else
-      t[p][q] = t[q][p] = cdivr(tau[s], sqrt2);
+      t[p][q] = t[q][p] = cdivr(tau[s], 1.4142135623730951);  // std::numbers::sqrt2_v<double>
 #endif
     }
   }
