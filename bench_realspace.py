@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cg-iters", type=int, default=0, help="also time this many CG iterations")
+    ap.add_argument("--real", action="store_true",
+                    help="real float64 fields through the r2c half-spectrum path (default: complex, like the reference)")
     args = ap.parse_args()
 
     import torch
@@ -57,31 +59,38 @@ def main():
     L = tuple(n * h for n, h in zip(shape, SPACING))
     op = RealSpaceOperator.from_process_group(shape, L, MU, NU, device=local_rank, exchange_mode=args.mode)
     gen = torch.Generator(device=dev).manual_seed(4000 + rank)
-    u = torch.zeros(op.real_shape + (2,), dtype=torch.float64, device=dev)
-    u[..., 0].normal_(generator=gen)                       # real field carried as complex (imag = 0)
-    u = torch.view_as_complex(u)
+    if args.real:
+        u = torch.randn(op.real_shape, dtype=torch.float64, device=dev, generator=gen)
+    else:
+        u = torch.zeros(op.real_shape + (2,), dtype=torch.float64, device=dev)
+        u[..., 0].normal_(generator=gen)                   # real field carried as complex (imag = 0)
+        u = torch.view_as_complex(u)
     F = torch.empty_like(u)
+    apply = op.apply_real if args.real else op.apply
+    cg = op.cg_solve_real if args.real else op.cg_solve
     stream = torch.cuda.current_stream()
     rdev = dev if world > 1 else None
 
     for _ in range(args.warmup):
-        op.apply(u, out=F)
+        apply(u, out=F)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        op.apply(u, out=F)
+        apply(u, out=F)
     e1.record(stream)
     barrier()
     ms = slab.max_over_ranks(e0.elapsed_time(e1) / args.steps, rdev)
     phases = {k: slab.max_over_ranks(v, rdev) for k, v in op.timings().items()}
     modes = args.edge ** 3
-    xbytes = op.exchange_bytes
+    xbytes = op.exchange_bytes_real if args.real else op.exchange_bytes
+    spectrum = (args.edge // 2 + 1) / args.edge if args.real else 1.0
     line = {
         "metric": "real-space apply (FFT -> modal K -> iFFT), applies/s", "value": 1e3 / ms, "unit": "applies/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "effective_gmodes_per_s": modes / (ms * 1e-3) / 1e9, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D Q8 {args.edge}^3 real-space apply, n0 slabs over {world} GPU(s)",
+                   "fields": "real float64, r2c half spectrum" if args.real else "complex128 (c2c, as the reference)",
                    "exchange": ["nccl send/recv + pack/unpack kernels", "fused peer-store kernel (CUDA IPC over NVLink)"][args.mode]
                    if world > 1 else "none (single GPU)"},
         "phases_ms_last_apply_max_over_ranks": phases,
@@ -90,17 +99,17 @@ def main():
             "fwd_gbs_per_gpu": xbytes / (phases["exchange_fwd"] * 1e-3) / 1e9,
             "bwd_gbs_per_gpu": xbytes / (phases["exchange_bwd"] * 1e-3) / 1e9,
             "frac_of_measured_peer_copy_770": xbytes / (phases["exchange_fwd"] * 1e-3) / 1e9 / PEER_GBS},
-        "modal_gbs": 96 * modes / world / (phases["modal"] * 1e-3) / 1e9,
+        "modal_gbs": 96 * modes * spectrum / world / (phases["modal"] * 1e-3) / 1e9,
     }
 
     if args.cg_iters > 0:
         # periodic inclusion-like right-hand side: b = A(u0) with zero-mean u0 (in the range of A)
-        b = op.apply(u - 0.0).clone()
+        b = apply(u - 0.0).clone()
         barrier()
-        op.cg_solve(b, rtol=0.0, max_iter=2, check_every=0)            # warm-up, allocates work vectors
+        cg(b, rtol=0.0, max_iter=2, check_every=0)                      # warm-up, allocates work vectors
         barrier()
         e0.record(stream)
-        x, iters, res = op.cg_solve(b, rtol=0.0, max_iter=args.cg_iters, check_every=0)
+        x, iters, res = cg(b, rtol=0.0, max_iter=args.cg_iters, check_every=0)
         e1.record(stream)
         barrier()
         cg_ms = slab.max_over_ranks(e0.elapsed_time(e1), rdev)

@@ -58,8 +58,10 @@ RS_SIGNATURES = {
     "bri17_rs_inverse_fft_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double, _vp]),
     "bri17_rs_plan_modal": (_vp, [_vp]),
     "bri17_rs_plan_last_timings": (C.c_int, [_vp, _f64p, C.c_int]),
-    "bri17_rs_plan_exchange_bytes": (C.c_int64, [_vp]),
+    "bri17_rs_plan_exchange_bytes": (C.c_int64, [_vp, C.c_int]),
     "bri17_cg_solve_f64": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _i32p, _f64p, _vp]),
+    "bri17_real_space_apply_real_f64": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "bri17_cg_solve_real_f64": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _i32p, _f64p, _vp]),
 }
 
 _lib = None

@@ -58,7 +58,6 @@ using bri17b200::fail;
 namespace {
 
 constexpr int MAX_RANKS = 16;
-constexpr int NUM_EVENTS = 8;
 
 // One family of equal-length row pieces to move: for c < ncomp, a < rows:
 //   dst[c*dst_cs + a*dst_rs + (0..len)] = scale * src[c*src_cs + a*src_rs + (0..len)]
@@ -128,6 +127,8 @@ __global__ void scale_kernel(double2 *x, long long n, double scale) {
 }
 
 // ---- CG vector kernels (K5): deterministic two-stage reductions, device scalars ----
+// Vectors are plain double arrays (a complex field is its interleaved doubles:
+// sum x.y over doubles = sum Re(x conj y)), processed as double2 when possible.
 constexpr int RED_CTAS = 1184;  // 148 SMs x 8
 constexpr int RED_THREADS = 256;
 
@@ -144,21 +145,23 @@ __device__ __forceinline__ double block_sum(double v) {
   return t;  // valid in thread 0
 }
 
-// partial[b] = sum over this CTA's elements of Re(x conj(y))
-__global__ void __launch_bounds__(RED_THREADS) cg_dot_kernel(const double2 *x, const double2 *y,
-                                                              long long n, double *partial) {
+// partial[b] = sum over this CTA's elements of x*y      (n2 = number of double2 pairs, tail = odd element)
+__global__ void __launch_bounds__(RED_THREADS) cg_dot_kernel(const double *x, const double *y, long long n,
+                                                              double *partial) {
+  const double2 *x2 = reinterpret_cast<const double2 *>(x), *y2 = reinterpret_cast<const double2 *>(y);
+  const long long n2 = n >> 1;
   double acc = 0.;
-  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n;
+  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n2;
        i += (long long)gridDim.x * RED_THREADS) {
-    const double2 a = x[i], b = y[i];
+    const double2 a = x2[i], b = y2[i];
     acc += a.x * b.x + a.y * b.y;
   }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc += x[n - 1] * y[n - 1];
   acc = block_sum(acc);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
-__global__ void __launch_bounds__(RED_THREADS) cg_finish_kernel(const double *partial, int n,
-                                                                 double *out) {
+__global__ void __launch_bounds__(RED_THREADS) cg_finish_kernel(const double *partial, int n, double *out) {
   double acc = 0.;
   for (int i = threadIdx.x; i < n; i += RED_THREADS) acc += partial[i];
   acc = block_sum(acc);
@@ -166,61 +169,91 @@ __global__ void __launch_bounds__(RED_THREADS) cg_finish_kernel(const double *pa
 }
 
 // alpha = rr/pAp;  x += alpha p;  r -= alpha Ap;  partial <r,r>   (fused axpy + axpy + dot)
-__global__ void __launch_bounds__(RED_THREADS) cg_update_kernel(double2 *x, double2 *r, const double2 *p,
-                                                                 const double2 *Ap, long long n,
-                                                                 const double *rr, const double *pAp,
-                                                                 double *partial) {
+__global__ void __launch_bounds__(RED_THREADS) cg_update_kernel(double *x, double *r, const double *p,
+                                                                 const double *Ap, long long n, const double *rr,
+                                                                 const double *pAp, double *partial) {
   const double alpha = *rr / *pAp;
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *A2 = reinterpret_cast<const double2 *>(Ap);
+  const long long n2 = n >> 1;
   double acc = 0.;
-  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n;
+  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n2;
        i += (long long)gridDim.x * RED_THREADS) {
-    const double2 pi = p[i], ai = Ap[i];
-    double2 xi = x[i], ri = r[i];
+    const double2 pi = p2[i], ai = A2[i];
+    double2 xi = x2[i], ri = r2[i];
     xi.x += alpha * pi.x; xi.y += alpha * pi.y;
     ri.x -= alpha * ai.x; ri.y -= alpha * ai.y;
-    x[i] = xi; r[i] = ri;
+    x2[i] = xi; r2[i] = ri;
     acc += ri.x * ri.x + ri.y * ri.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    x[n - 1] += alpha * p[n - 1];
+    const double t = r[n - 1] - alpha * Ap[n - 1];
+    r[n - 1] = t;
+    acc += t * t;
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
 // beta = rr_new/rr;  p = r + beta p
-__global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double2 *p, const double2 *r, long long n,
+__global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double *p, const double *r, long long n,
                                                                     const double *rr_new, const double *rr) {
   const double beta = *rr_new / *rr;
-  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n;
+  double2 *p2 = reinterpret_cast<double2 *>(p);
+  const double2 *r2 = reinterpret_cast<const double2 *>(r);
+  const long long n2 = n >> 1;
+  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n2;
        i += (long long)gridDim.x * RED_THREADS) {
-    const double2 ri = r[i];
-    double2 pi = p[i];
+    const double2 ri = r2[i];
+    double2 pi = p2[i];
     pi.x = ri.x + beta * pi.x; pi.y = ri.y + beta * pi.y;
-    p[i] = pi;
+    p2[i] = pi;
   }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
 }
 
 }  // namespace
+
+// Geometry + cuFFT plans of one spectral layout.  "complex": the reference's c2c
+// transforms (tests/test_bri17.cpp:117-127).  "real": r2c/c2r over the trailing
+// axes, only the non-redundant half spectrum of the last axis is kept
+// (K^(N-k) = K^(k)).
+struct Layout {
+  bool real = false, ready = false;
+  int S1 = 1, S2e = 1;        // spectral extents of axis 1 and of the trailing axis (1 in 2-D)
+  int k1_beg[16 + 1] = {};
+  int n1_loc = 0;
+  int64_t t_count = 0;        // complex elements / component after the local transform [n0_loc][S1][S2e]
+  int64_t fourier_count = 0;  // ... of the Fourier-side block [N0][n1_loc][S2e]
+  cufftHandle fwd_local = 0, inv_local = 0, axis0 = 0;
+  bool have_local = false, have_axis0 = false;
+};
 
 struct bri17_rs_plan {
   int dim = 0, shape[3] = {1, 1, 1};
   double L[3] = {1, 1, 1};
   int device = 0, rank = 0, nranks = 1, mode = 0;
-  int N2e = 1;                 // trailing extent (N2 in 3-D, 1 in 2-D)
-  int n0_beg[MAX_RANKS + 1], k1_beg[MAX_RANKS + 1];
-  int n0_loc = 0, n1_loc = 0;
-  int64_t real_count = 0, fourier_count = 0;
+  int N2e = 1;                 // trailing extent in real space (N2 in 3-D, 1 in 2-D)
+  int n0_beg[16 + 1];
+  int n0_loc = 0;
+  int64_t real_count = 0;      // elements / component of the real-space slab [n0_loc][N1][N2e]
   double correction = 1.0;     // |h|/|N|, tests/test_bri17.cpp:93-98
+  Layout lc, lr;               // complex (c2c) and real (r2c) layouts
   bri17_plan *modal = nullptr;
-  cufftHandle fft_local = 0, fft_axis0 = 0;
-  bool have_local = false, have_axis0 = false;
   ncclComm_t comm = nullptr;
-  double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components each
-  double2 *peerW[MAX_RANKS] = {}, *peerW2[MAX_RANKS] = {};
+  double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components of the c2c layout each
+  size_t buf_bytes = 0;
+  int64_t real_upper = 0;      // element offset of the upper region of W2 used by the real path
+  double2 *peerW[16] = {}, *peerW2[16] = {};
   double *barrier_word = nullptr;
-  cudaEvent_t ev[NUM_EVENTS + 1] = {};
+  cudaEvent_t ev[8 + 1] = {};
   bool timings_valid = false;
-  // CG work space
-  double2 *cg_r = nullptr, *cg_p = nullptr, *cg_Ap = nullptr;
+  // CG work space (doubles)
+  double *cg_r = nullptr, *cg_p = nullptr, *cg_Ap = nullptr;
+  size_t cg_len = 0;
   double *cg_partial = nullptr, *cg_scalars = nullptr;
+  double *rbuf = nullptr;      // staging for real components that are not 16-byte aligned (odd slab sizes)
 };
 
 namespace {
@@ -253,39 +286,39 @@ int stream_barrier(bri17_rs_plan *p, cudaStream_t st) {
   return BRI17_OK;
 }
 
-// Forward exchange: real-space layout T[c][a][b][k2] -> Fourier-side layout X[c][n0][b_loc][k2].
-// `S` is the packed send buffer (mode 0).  ncomp <= dim.
-int exchange_forward(bri17_rs_plan *p, const double2 *T, double2 *X, double2 *S, int ncomp,
+// Forward exchange: local-transform layout T[c][a][b][k2] (a in my n0 slab, b over S1)
+// -> Fourier-side layout X[c][n0][b_loc][k2].  `S` is the packed send buffer (mode 0).
+int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double2 *X, double2 *S, int ncomp,
                      cudaStream_t st) {
-  const int P = p->nranks, r = p->rank, N0 = p->shape[0], N1 = p->shape[1], N2e = p->N2e;
+  const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   CopyPlan cp{};
   cp.ncomp = ncomp;
   cp.scale = 1.0;
   std::vector<long long> off(P + 1, 0);  // packed offsets (elements)
   for (int q = 0; q < P; q++)
-    off[q + 1] = off[q] + (long long)ncomp * p->n0_loc * (p->k1_beg[q + 1] - p->k1_beg[q]) * N2e;
+    off[q + 1] = off[q] + (long long)ncomp * p->n0_loc * (l.k1_beg[q + 1] - l.k1_beg[q]) * S2e;
   int maxlen = 0;
   for (int i = 1; i <= P; i++) {
     const int q = (r + i) % P;
-    const int n1q = p->k1_beg[q + 1] - p->k1_beg[q];
+    const int n1q = l.k1_beg[q + 1] - l.k1_beg[q];
     if (n1q == 0 || p->n0_loc == 0) continue;
     CopySeg &g = cp.seg[cp.nseg++];
-    g.src = T + (long long)p->k1_beg[q] * N2e;
-    g.src_cs = (long long)p->n0_loc * N1 * N2e;
-    g.src_rs = (long long)N1 * N2e;
+    g.src = T + (long long)l.k1_beg[q] * S2e;
+    g.src_cs = (long long)p->n0_loc * S1 * S2e;
+    g.src_rs = (long long)S1 * S2e;
     g.rows = p->n0_loc;
-    g.len = n1q * N2e;
+    g.len = n1q * S2e;
     maxlen = std::max(maxlen, g.len);
     const bool direct = (q == r) || p->mode == 1;  // store at the final position
     if (direct) {
       double2 *base = (q == r) ? X : p->peerW[q];
-      g.dst = base + (long long)p->n0_beg[r] * n1q * N2e;
-      g.dst_cs = (long long)N0 * n1q * N2e;
-      g.dst_rs = (long long)n1q * N2e;
+      g.dst = base + (long long)p->n0_beg[r] * n1q * S2e;
+      g.dst_cs = (long long)N0 * n1q * S2e;
+      g.dst_rs = (long long)n1q * S2e;
     } else {
       g.dst = S + off[q];
-      g.dst_cs = (long long)p->n0_loc * n1q * N2e;
-      g.dst_rs = (long long)n1q * N2e;
+      g.dst_cs = (long long)p->n0_loc * n1q * S2e;
+      g.dst_rs = (long long)n1q * S2e;
     }
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * p->n0_loc * P);
@@ -296,12 +329,12 @@ int exchange_forward(bri17_rs_plan *p, const double2 *T, double2 *X, double2 *S,
   RS_NCCL_TRY(ncclGroupStart());
   for (int q = 0; q < P; q++) {
     if (q == r) continue;
-    const long long n1q = p->k1_beg[q + 1] - p->k1_beg[q], n0q = p->n0_beg[q + 1] - p->n0_beg[q];
+    const long long n1q = l.k1_beg[q + 1] - l.k1_beg[q], n0q = p->n0_beg[q + 1] - p->n0_beg[q];
     for (int c = 0; c < ncomp; c++) {
-      const long long scount = (long long)p->n0_loc * n1q * N2e, rcount = n0q * p->n1_loc * N2e;
+      const long long scount = (long long)p->n0_loc * n1q * S2e, rcount = n0q * l.n1_loc * S2e;
       if (scount) RS_NCCL_TRY(ncclSend(S + off[q] + c * scount, size_t(2 * scount), ncclDouble, q, p->comm, st));
       if (rcount)
-        RS_NCCL_TRY(ncclRecv(X + ((long long)c * N0 + p->n0_beg[q]) * p->n1_loc * N2e, size_t(2 * rcount),
+        RS_NCCL_TRY(ncclRecv(X + ((long long)c * N0 + p->n0_beg[q]) * l.n1_loc * S2e, size_t(2 * rcount),
                              ncclDouble, q, p->comm, st));
     }
   }
@@ -309,11 +342,11 @@ int exchange_forward(bri17_rs_plan *p, const double2 *T, double2 *X, double2 *S,
   return BRI17_OK;
 }
 
-// Backward exchange: Fourier-side X[c][n0][b_loc][k2] -> real-space layout D[c][a][b][k2] (times scale).
+// Backward exchange: Fourier-side X[c][n0][b_loc][k2] -> local-transform layout D[c][a][b][k2] (times scale).
 // mode 0: R = packed receive buffer, D written by the unpack; mode 1: peers store into our W2 (= D).
-int exchange_backward(bri17_rs_plan *p, const double2 *X, double2 *D, double2 *R, int ncomp, double scale,
-                      cudaStream_t st) {
-  const int P = p->nranks, r = p->rank, N0 = p->shape[0], N1 = p->shape[1], N2e = p->N2e;
+int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, double2 *D, double2 *R, int ncomp,
+                      double scale, cudaStream_t st) {
+  const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   if (p->mode == 1 || P == 1) {
     // every row (c, n0) goes, whole, to the owner of n0, at its final position
     CopyPlan cp{};
@@ -322,34 +355,34 @@ int exchange_backward(bri17_rs_plan *p, const double2 *X, double2 *D, double2 *R
     for (int i = 1; i <= P; i++) {
       const int q = (r + i) % P;
       const int n0q = p->n0_beg[q + 1] - p->n0_beg[q];
-      if (n0q == 0 || p->n1_loc == 0) continue;
+      if (n0q == 0 || l.n1_loc == 0) continue;
       CopySeg &g = cp.seg[cp.nseg++];
-      g.src = X + (long long)p->n0_beg[q] * p->n1_loc * N2e;
-      g.src_cs = (long long)N0 * p->n1_loc * N2e;
-      g.src_rs = (long long)p->n1_loc * N2e;
+      g.src = X + (long long)p->n0_beg[q] * l.n1_loc * S2e;
+      g.src_cs = (long long)N0 * l.n1_loc * S2e;
+      g.src_rs = (long long)l.n1_loc * S2e;
       g.rows = n0q;
-      g.len = p->n1_loc * N2e;
+      g.len = l.n1_loc * S2e;
       double2 *base = (q == r) ? D : p->peerW2[q];
-      g.dst = base + (long long)p->k1_beg[r] * N2e;
-      g.dst_cs = (long long)n0q * N1 * N2e;
-      g.dst_rs = (long long)N1 * N2e;
+      g.dst = base + (long long)l.k1_beg[r] * S2e;
+      g.dst_cs = (long long)n0q * S1 * S2e;
+      g.dst_rs = (long long)S1 * S2e;
     }
-    cp.parts = choose_parts(p->n1_loc * N2e, (long long)ncomp * N0);
+    cp.parts = choose_parts(l.n1_loc * S2e, (long long)ncomp * N0);
     RS_TRY(stream_barrier(p, st));
     RS_TRY(launch_copy(cp, P > 1, st));
     return stream_barrier(p, st);
   }
   std::vector<long long> off(P + 1, 0);
   for (int q = 0; q < P; q++)
-    off[q + 1] = off[q] + (long long)ncomp * p->n0_loc * (p->k1_beg[q + 1] - p->k1_beg[q]) * N2e;
+    off[q + 1] = off[q] + (long long)ncomp * p->n0_loc * (l.k1_beg[q + 1] - l.k1_beg[q]) * S2e;
   RS_NCCL_TRY(ncclGroupStart());
   for (int q = 0; q < P; q++) {
     if (q == r) continue;
-    const long long n1q = p->k1_beg[q + 1] - p->k1_beg[q], n0q = p->n0_beg[q + 1] - p->n0_beg[q];
+    const long long n1q = l.k1_beg[q + 1] - l.k1_beg[q], n0q = p->n0_beg[q + 1] - p->n0_beg[q];
     for (int c = 0; c < ncomp; c++) {
-      const long long scount = n0q * p->n1_loc * N2e, rcount = (long long)p->n0_loc * n1q * N2e;
+      const long long scount = n0q * l.n1_loc * S2e, rcount = (long long)p->n0_loc * n1q * S2e;
       if (scount)
-        RS_NCCL_TRY(ncclSend(X + ((long long)c * N0 + p->n0_beg[q]) * p->n1_loc * N2e, size_t(2 * scount),
+        RS_NCCL_TRY(ncclSend(X + ((long long)c * N0 + p->n0_beg[q]) * l.n1_loc * S2e, size_t(2 * scount),
                              ncclDouble, q, p->comm, st));
       if (rcount) RS_NCCL_TRY(ncclRecv(R + off[q] + c * rcount, size_t(2 * rcount), ncclDouble, q, p->comm, st));
     }
@@ -360,49 +393,51 @@ int exchange_backward(bri17_rs_plan *p, const double2 *X, double2 *D, double2 *R
   cp.scale = scale;
   int maxlen = 0;
   for (int q = 0; q < P; q++) {
-    const int n1q = p->k1_beg[q + 1] - p->k1_beg[q];
+    const int n1q = l.k1_beg[q + 1] - l.k1_beg[q];
     if (n1q == 0 || p->n0_loc == 0) continue;
     CopySeg &g = cp.seg[cp.nseg++];
     g.rows = p->n0_loc;
-    g.len = n1q * N2e;
+    g.len = n1q * S2e;
     maxlen = std::max(maxlen, g.len);
     if (q == r) {  // own block straight from X
-      g.src = X + (long long)p->n0_beg[r] * n1q * N2e;
-      g.src_cs = (long long)N0 * n1q * N2e;
-      g.src_rs = (long long)n1q * N2e;
+      g.src = X + (long long)p->n0_beg[r] * n1q * S2e;
+      g.src_cs = (long long)N0 * n1q * S2e;
+      g.src_rs = (long long)n1q * S2e;
     } else {
       g.src = R + off[q];
-      g.src_cs = (long long)p->n0_loc * n1q * N2e;
-      g.src_rs = (long long)n1q * N2e;
+      g.src_cs = (long long)p->n0_loc * n1q * S2e;
+      g.src_rs = (long long)n1q * S2e;
     }
-    g.dst = D + (long long)p->k1_beg[q] * N2e;
-    g.dst_cs = (long long)p->n0_loc * N1 * N2e;
-    g.dst_rs = (long long)N1 * N2e;
+    g.dst = D + (long long)l.k1_beg[q] * S2e;
+    g.dst_cs = (long long)p->n0_loc * S1 * S2e;
+    g.dst_rs = (long long)S1 * S2e;
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * p->n0_loc * P);
   return launch_copy(cp, 0, st);
 }
 
-int fft_local(bri17_rs_plan *p, const double2 *in, double2 *out, int ncomp, int dir, cudaStream_t st) {
-  if (!p->have_local || p->n0_loc == 0) {
-    if (in != out && p->real_count)
-      BRI17_CUDA_TRY(cudaMemcpyAsync(out, in, sizeof(double2) * ncomp * p->real_count,
-                                     cudaMemcpyDeviceToDevice, st));
+// c2c local transform over the trailing axes (complex layout only)
+int fft_local_c2c(bri17_rs_plan *p, const double2 *in, double2 *out, int ncomp, int dir, cudaStream_t st) {
+  const Layout &l = p->lc;
+  if (!l.have_local) {
+    if (in != out && l.t_count)
+      BRI17_CUDA_TRY(cudaMemcpyAsync(out, in, sizeof(double2) * ncomp * l.t_count, cudaMemcpyDeviceToDevice, st));
     return BRI17_OK;
   }
-  RS_CUFFT_TRY(cufftSetStream(p->fft_local, st));
+  RS_CUFFT_TRY(cufftSetStream(l.fwd_local, st));
   for (int c = 0; c < ncomp; c++)
-    RS_CUFFT_TRY(cufftExecZ2Z(p->fft_local, (cufftDoubleComplex *)(in + c * p->real_count),
-                              (cufftDoubleComplex *)(out + c * p->real_count), dir));
+    RS_CUFFT_TRY(cufftExecZ2Z(l.fwd_local, (cufftDoubleComplex *)(in + c * l.t_count),
+                              (cufftDoubleComplex *)(out + c * l.t_count), dir));
   return BRI17_OK;
 }
 
-int fft_axis0(bri17_rs_plan *p, double2 *x, int ncomp, int dir, cudaStream_t st) {
-  if (!p->have_axis0 || p->n1_loc == 0) return BRI17_OK;
-  RS_CUFFT_TRY(cufftSetStream(p->fft_axis0, st));
+int fft_axis0(bri17_rs_plan *p, const Layout &l, double2 *x, int ncomp, int dir, cudaStream_t st) {
+  (void)p;
+  if (!l.have_axis0) return BRI17_OK;
+  RS_CUFFT_TRY(cufftSetStream(l.axis0, st));
   for (int c = 0; c < ncomp; c++)
-    RS_CUFFT_TRY(cufftExecZ2Z(p->fft_axis0, (cufftDoubleComplex *)(x + c * p->fourier_count),
-                              (cufftDoubleComplex *)(x + c * p->fourier_count), dir));
+    RS_CUFFT_TRY(cufftExecZ2Z(l.axis0, (cufftDoubleComplex *)(x + c * l.fourier_count),
+                              (cufftDoubleComplex *)(x + c * l.fourier_count), dir));
   return BRI17_OK;
 }
 
@@ -418,6 +453,147 @@ struct DeviceGuard {
 };
 
 void mark(bri17_rs_plan *p, int i, cudaStream_t st) { cudaEventRecord(p->ev[i], st); }
+
+// Geometry of a layout (no cuFFT plan yet).
+void layout_geometry(const bri17_rs_plan *p, Layout &l, bool real) {
+  const int dim = p->dim, P = p->nranks;
+  l.real = real;
+  const int last = p->shape[dim - 1];
+  if (dim == 3) { l.S1 = p->shape[1]; l.S2e = real ? last / 2 + 1 : last; }
+  else { l.S1 = real ? last / 2 + 1 : last; l.S2e = 1; }
+  for (int q = 0; q <= P; q++) l.k1_beg[q] = int((int64_t)q * l.S1 / P);
+  l.n1_loc = l.k1_beg[p->rank + 1] - l.k1_beg[p->rank];
+  l.t_count = (int64_t)p->n0_loc * l.S1 * l.S2e;
+  l.fourier_count = (int64_t)p->shape[0] * l.n1_loc * l.S2e;
+}
+
+// cuFFT plans of a layout whose geometry is set.
+int setup_layout(bri17_rs_plan *p, Layout &l) {
+  const int dim = p->dim;
+  const bool real = l.real;
+  size_t ws = 0;
+  if (p->n0_loc > 0) {  // local transform over the trailing axes, one slab plane per batch entry
+    long long n64[2] = {p->shape[1], p->N2e};
+    const int frank = dim - 1;
+    const long long rplane = (long long)p->shape[1] * p->N2e, splane = (long long)l.S1 * l.S2e;
+    if (!real) {
+      RS_CUFFT_TRY(cufftCreate(&l.fwd_local));
+      RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local, frank, n64, nullptr, 1, rplane, nullptr, 1, rplane,
+                                       CUFFT_Z2Z, p->n0_loc, &ws));
+      l.inv_local = l.fwd_local;
+    } else {
+      RS_CUFFT_TRY(cufftCreate(&l.fwd_local));
+      RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local, frank, n64, nullptr, 1, rplane, nullptr, 1, splane,
+                                       CUFFT_D2Z, p->n0_loc, &ws));
+      RS_CUFFT_TRY(cufftCreate(&l.inv_local));
+      RS_CUFFT_TRY(cufftMakePlanMany64(l.inv_local, frank, n64, nullptr, 1, splane, nullptr, 1, rplane,
+                                       CUFFT_Z2D, p->n0_loc, &ws));
+    }
+    l.have_local = true;
+  }
+  if (l.n1_loc > 0) {  // axis 0 on the Fourier-side block: stride = batch = n1_loc*S2e
+    const long long S = (long long)l.n1_loc * l.S2e;
+    long long n64[1] = {p->shape[0]}, embed[1] = {p->shape[0]};
+    RS_CUFFT_TRY(cufftCreate(&l.axis0));
+    RS_CUFFT_TRY(cufftMakePlanMany64(l.axis0, 1, n64, embed, S, 1, embed, S, 1, CUFFT_Z2Z, S, &ws));
+    l.have_axis0 = true;
+  }
+  l.ready = true;
+  return BRI17_OK;
+}
+
+void destroy_layout(Layout &l) {
+  if (l.have_local) {
+    cufftDestroy(l.fwd_local);
+    if (l.real) cufftDestroy(l.inv_local);
+  }
+  if (l.have_axis0) cufftDestroy(l.axis0);
+  l = Layout{};
+}
+
+// Exchange buffers: always present for P > 1 (allocated at creation so that their IPC
+// handles can be exchanged); for P == 1 only the real path needs one (lazily).
+int ensure_buffers(bri17_rs_plan *p, size_t bytes) {
+  if (p->buf_bytes >= bytes) return BRI17_OK;
+  if (p->nranks > 1) return fail(BRI17_ERR_UNSUPPORTED, "exchange buffers cannot grow after creation");
+  if (p->W2) cudaFree(p->W2);
+  p->W2 = nullptr;
+  BRI17_CUDA_TRY(cudaMalloc(&p->W2, bytes));
+  p->buf_bytes = bytes;
+  return BRI17_OK;
+}
+
+// The modal operator on the Fourier-side block of a layout, in place, scaled by |h|/|N|.
+int modal_on_block(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st) {
+  if (l.fourier_count == 0) return BRI17_OK;
+  int kb[3] = {0, l.k1_beg[p->rank], 0};
+  int ls[3] = {p->shape[0], l.n1_loc, l.S2e};
+  return bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st);
+}
+
+// Shared CG driver over double arrays; `apply(d, Ad)` is the operator.
+template <typename Apply>
+int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long n, double rtol, int max_iter,
+            int check_every, int *iterations, double *rel_residual, cudaStream_t st) {
+  const size_t bytes = sizeof(double) * std::max<long long>(n, 2);
+  if (p->cg_len < bytes) {
+    for (double *ptr : {p->cg_r, p->cg_p, p->cg_Ap})
+      if (ptr) cudaFree(ptr);
+    p->cg_r = p->cg_p = p->cg_Ap = nullptr;
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_r, bytes));
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_p, bytes));
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_Ap, bytes));
+    p->cg_len = bytes;
+  }
+  if (!p->cg_partial) {
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_partial, sizeof(double) * RED_CTAS));
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_scalars, sizeof(double) * 8));
+  }
+  double *r = p->cg_r, *d = p->cg_p, *Ad = p->cg_Ap;
+  double *sc = p->cg_scalars;  // [0] rr (even iter) [1] rr (odd iter) [2] pAp [3] bb
+  auto reduce_to = [&](double *slot) -> int {
+    cg_finish_kernel<<<1, RED_THREADS, 0, st>>>(p->cg_partial, RED_CTAS, slot);
+    if (p->nranks > 1) RS_NCCL_TRY(ncclAllReduce(slot, slot, 1, ncclDouble, ncclSum, p->comm, st));
+    return BRI17_OK;
+  };
+  const size_t vbytes = sizeof(double) * n;
+  BRI17_CUDA_TRY(cudaMemsetAsync(x, 0, vbytes, st));
+  BRI17_CUDA_TRY(cudaMemcpyAsync(r, b, vbytes, cudaMemcpyDeviceToDevice, st));
+  BRI17_CUDA_TRY(cudaMemcpyAsync(d, b, vbytes, cudaMemcpyDeviceToDevice, st));
+  cg_dot_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(r, r, n, p->cg_partial);
+  RS_TRY(reduce_to(sc + 0));
+  double bb = 0.;
+  BRI17_CUDA_TRY(cudaMemcpyAsync(&bb, sc + 0, sizeof(double), cudaMemcpyDeviceToHost, st));
+  BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+  int it = 0;
+  double rr_host = bb;
+  if (bb > 0.) {
+    for (; it < max_iter;) {
+      double *rr = sc + (it & 1), *rr_new = sc + ((it + 1) & 1);
+      RS_TRY(apply(d, Ad));
+      cg_dot_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(d, Ad, n, p->cg_partial);
+      RS_TRY(reduce_to(sc + 2));
+      cg_update_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(x, r, d, Ad, n, rr, sc + 2, p->cg_partial);
+      RS_TRY(reduce_to(rr_new));
+      cg_direction_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(d, r, n, rr_new, rr);
+      it++;
+      if (check_every > 0 && (it % check_every == 0 || it == max_iter)) {
+        BRI17_CUDA_TRY(cudaMemcpyAsync(&rr_host, rr_new, sizeof(double), cudaMemcpyDeviceToHost, st));
+        BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+        if (rr_host <= rtol * rtol * bb) break;
+      }
+    }
+    if (check_every <= 0) {
+      BRI17_CUDA_TRY(cudaMemcpyAsync(&rr_host, sc + (it & 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+      BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(BRI17_ERR_CUDA, std::string("CG: ") + cudaGetErrorString(e));
+  if (iterations) *iterations = it;
+  if (rel_residual) *rel_residual = bb > 0. ? std::sqrt(rr_host / bb) : 0.;
+  return BRI17_OK;
+}
 
 }  // namespace
 
@@ -442,10 +618,10 @@ int bri17_rs_plan_destroy(bri17_rs_plan *p) {
     if (p->peerW2[q]) cudaIpcCloseMemHandle(p->peerW2[q]);
   }
   if (p->comm) ncclCommDestroy(p->comm);
-  if (p->have_local) cufftDestroy(p->fft_local);
-  if (p->have_axis0) cufftDestroy(p->fft_axis0);
+  destroy_layout(p->lc);
+  destroy_layout(p->lr);
   for (void *ptr : {(void *)p->W, (void *)p->W2, (void *)p->barrier_word, (void *)p->cg_r, (void *)p->cg_p,
-                    (void *)p->cg_Ap, (void *)p->cg_partial, (void *)p->cg_scalars})
+                    (void *)p->cg_Ap, (void *)p->cg_partial, (void *)p->cg_scalars, (void *)p->rbuf})
     if (ptr) cudaFree(ptr);
   for (auto &e : p->ev)
     if (e) cudaEventDestroy(e);
@@ -483,14 +659,9 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
   }
   p->correction = cell_volume / double(size);  // :98
   p->N2e = dim == 3 ? shape[2] : 1;
-  for (int q = 0; q <= nranks; q++) {
-    p->n0_beg[q] = int((int64_t)q * shape[0] / nranks);
-    p->k1_beg[q] = int((int64_t)q * shape[1] / nranks);
-  }
+  for (int q = 0; q <= nranks; q++) p->n0_beg[q] = int((int64_t)q * shape[0] / nranks);
   p->n0_loc = p->n0_beg[rank + 1] - p->n0_beg[rank];
-  p->n1_loc = p->k1_beg[rank + 1] - p->k1_beg[rank];
   p->real_count = (int64_t)p->n0_loc * shape[1] * p->N2e;
-  p->fourier_count = (int64_t)shape[0] * p->n1_loc * p->N2e;
 
   int rc = bri17_plan_create(&p->modal, dim, shape, L, mu, nu, device);
   if (rc) { delete p; return rc; }
@@ -499,44 +670,25 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
 
   for (auto &e : p->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(BRI17_ERR_CUDA, "cudaEventCreate failed"));
-
-  // local transform over the trailing axes, one plane of the slab per batch entry
-  if (p->n0_loc > 0) {
-    int n[2] = {shape[1], p->N2e};
-    const int frank = dim - 1;
-    const long long plane = (long long)shape[1] * p->N2e;
-    cufftResult cr = cufftCreate(&p->fft_local);
-    size_t ws = 0;
-    long long n64[2] = {n[0], n[1]};
-    if (cr == CUFFT_SUCCESS)
-      cr = cufftMakePlanMany64(p->fft_local, frank, n64, nullptr, 1, plane, nullptr, 1, plane, CUFFT_Z2Z,
-                               p->n0_loc, &ws);
-    if (cr != CUFFT_SUCCESS) return bail(fail(BRI17_ERR_CUDA, "cuFFT local plan failed: " + std::to_string(int(cr))));
-    p->have_local = true;
-  }
-  // transform along axis 0 on the Fourier-side block: stride = n1_loc*N2e, batch = n1_loc*N2e
-  if (p->n1_loc > 0) {
-    const long long S = (long long)p->n1_loc * p->N2e;
-    long long n64[1] = {shape[0]};
-    long long embed[1] = {shape[0]};
-    size_t ws = 0;
-    cufftResult cr = cufftCreate(&p->fft_axis0);
-    if (cr == CUFFT_SUCCESS)
-      cr = cufftMakePlanMany64(p->fft_axis0, 1, n64, embed, S, 1, embed, S, 1, CUFFT_Z2Z, S, &ws);
-    if (cr != CUFFT_SUCCESS) return bail(fail(BRI17_ERR_CUDA, "cuFFT axis-0 plan failed: " + std::to_string(int(cr))));
-    p->have_axis0 = true;
-  }
+  layout_geometry(p, p->lc, false);
+  layout_geometry(p, p->lr, true);
+  // the real path keeps its local-transform data in the lower part of W2 and its packed
+  // send/receive pieces (NCCL mode) above it
+  p->real_upper = int64_t(dim) * std::max(p->lr.t_count, p->lr.fourier_count);
+  if ((rc = setup_layout(p, p->lc))) return bail(rc);
 
   if (nranks > 1) {
     ncclUniqueId id;
     std::memcpy(&id, nccl_unique_id, sizeof(id));
     ncclResult_t nr = ncclCommInitRank(&p->comm, nranks, id, rank);
     if (nr != ncclSuccess) return bail(fail(BRI17_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(nr)));
-    const size_t cap = sizeof(double2) * dim * size_t(std::max(p->real_count, p->fourier_count));
-    if (cudaMalloc(&p->W, std::max<size_t>(cap, 16)) != cudaSuccess ||
-        cudaMalloc(&p->W2, std::max<size_t>(cap, 16)) != cudaSuccess ||
+    const size_t cap = std::max<size_t>(
+        sizeof(double2) * std::max<size_t>(size_t(dim) * size_t(std::max(p->lc.t_count, p->lc.fourier_count)),
+                                           2 * size_t(p->real_upper)), 16);
+    if (cudaMalloc(&p->W, cap) != cudaSuccess || cudaMalloc(&p->W2, cap) != cudaSuccess ||
         cudaMalloc(&p->barrier_word, 256) != cudaSuccess)
       return bail(fail(BRI17_ERR_CUDA, "exchange buffer allocation failed"));
+    p->buf_bytes = cap;
     cudaMemset(p->barrier_word, 0, 256);
     if (p->mode == 1) {
       // exchange CUDA-IPC handles of W and W2 through NCCL itself
@@ -574,18 +726,18 @@ int bri17_rs_plan_local(const bri17_rs_plan *p, int *n0_begin, int *n0_count, in
   if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");
   if (n0_begin) *n0_begin = p->n0_beg[p->rank];
   if (n0_count) *n0_count = p->n0_loc;
-  if (k1_begin) *k1_begin = p->k1_beg[p->rank];
-  if (k1_count) *k1_count = p->n1_loc;
+  if (k1_begin) *k1_begin = p->lc.k1_beg[p->rank];
+  if (k1_count) *k1_count = p->lc.n1_loc;
   return BRI17_OK;
 }
 int64_t bri17_rs_plan_real_count(const bri17_rs_plan *p) { return p ? p->real_count : -1; }
-int64_t bri17_rs_plan_fourier_count(const bri17_rs_plan *p) { return p ? p->fourier_count : -1; }
+int64_t bri17_rs_plan_fourier_count(const bri17_rs_plan *p) { return p ? p->lc.fourier_count : -1; }
 bri17_plan *bri17_rs_plan_modal(bri17_rs_plan *p) { return p ? p->modal : nullptr; }
 
-int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *p) {
+int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *p, int real_layout) {
   if (!p) return -1;
-  const int64_t others = p->shape[1] - p->n1_loc;
-  return int64_t(16) * p->dim * p->n0_loc * others * p->N2e;
+  const Layout *l = real_layout ? &p->lr : &p->lc;
+  return int64_t(16) * p->dim * p->n0_loc * (l->S1 - l->n1_loc) * l->S2e;
 }
 
 int bri17_rs_forward_fft_f64(bri17_rs_plan *p, const void *x_dev, void *x_hat_dev, int ncomp, void *stream) {
@@ -593,23 +745,24 @@ int bri17_rs_forward_fft_f64(bri17_rs_plan *p, const void *x_dev, void *x_hat_de
   if (ncomp < 1) return fail(BRI17_ERR_INVALID_ARG, "ncomp < 1");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
+  const Layout &l = p->lc;
   const double2 *x = static_cast<const double2 *>(x_dev);
   double2 *xh = static_cast<double2 *>(x_hat_dev);
   if (p->nranks == 1) {
-    RS_TRY(fft_local(p, x, xh, ncomp, CUFFT_FORWARD, st));
-    return fft_axis0(p, xh, ncomp, CUFFT_FORWARD, st);
+    RS_TRY(fft_local_c2c(p, x, xh, ncomp, CUFFT_FORWARD, st));
+    return fft_axis0(p, l, xh, ncomp, CUFFT_FORWARD, st);
   }
   for (int c0 = 0; c0 < ncomp; c0 += p->dim) {  // the exchange buffers hold dim components
     const int nc = std::min(p->dim, ncomp - c0);
-    RS_TRY(fft_local(p, x + c0 * p->real_count, p->W2, nc, CUFFT_FORWARD, st));
-    double2 *X = xh + c0 * p->fourier_count;
+    RS_TRY(fft_local_c2c(p, x + c0 * l.t_count, p->W2, nc, CUFFT_FORWARD, st));
+    double2 *X = xh + c0 * l.fourier_count;
     if (p->mode == 1) {  // peers store into our W: stage through it
-      RS_TRY(exchange_forward(p, p->W2, p->W, nullptr, nc, st));
-      BRI17_CUDA_TRY(cudaMemcpyAsync(X, p->W, sizeof(double2) * nc * p->fourier_count, cudaMemcpyDeviceToDevice, st));
+      RS_TRY(exchange_forward(p, l, p->W2, p->W, nullptr, nc, st));
+      BRI17_CUDA_TRY(cudaMemcpyAsync(X, p->W, sizeof(double2) * nc * l.fourier_count, cudaMemcpyDeviceToDevice, st));
     } else {
-      RS_TRY(exchange_forward(p, p->W2, X, p->W, nc, st));
+      RS_TRY(exchange_forward(p, l, p->W2, X, p->W, nc, st));
     }
-    RS_TRY(fft_axis0(p, X, nc, CUFFT_FORWARD, st));
+    RS_TRY(fft_axis0(p, l, X, nc, CUFFT_FORWARD, st));
   }
   return BRI17_OK;
 }
@@ -619,25 +772,26 @@ int bri17_rs_inverse_fft_f64(bri17_rs_plan *p, void *x_hat_dev, void *x_dev, int
   if (ncomp < 1) return fail(BRI17_ERR_INVALID_ARG, "ncomp < 1");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
+  const Layout &l = p->lc;
   double2 *x = static_cast<double2 *>(x_dev);
   double2 *xh = static_cast<double2 *>(x_hat_dev);
   if (p->nranks == 1) {
-    RS_TRY(fft_axis0(p, xh, ncomp, CUFFT_INVERSE, st));
-    RS_TRY(fft_local(p, xh, x, ncomp, CUFFT_INVERSE, st));
-    if (scale != 1.0 && p->real_count)
-      scale_kernel<<<1184, 256, 0, st>>>(x, (long long)ncomp * p->real_count, scale);
+    RS_TRY(fft_axis0(p, l, xh, ncomp, CUFFT_INVERSE, st));
+    RS_TRY(fft_local_c2c(p, xh, x, ncomp, CUFFT_INVERSE, st));
+    if (scale != 1.0 && l.t_count)
+      scale_kernel<<<1184, 256, 0, st>>>(x, (long long)ncomp * l.t_count, scale);
     return BRI17_OK;
   }
   for (int c0 = 0; c0 < ncomp; c0 += p->dim) {
     const int nc = std::min(p->dim, ncomp - c0);
-    double2 *X = xh + c0 * p->fourier_count, *D = x + c0 * p->real_count;
-    RS_TRY(fft_axis0(p, X, nc, CUFFT_INVERSE, st));
+    double2 *X = xh + c0 * l.fourier_count, *D = x + c0 * l.t_count;
+    RS_TRY(fft_axis0(p, l, X, nc, CUFFT_INVERSE, st));
     if (p->mode == 1) {
-      RS_TRY(exchange_backward(p, X, p->W2, nullptr, nc, scale, st));
-      RS_TRY(fft_local(p, p->W2, D, nc, CUFFT_INVERSE, st));
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, nc, scale, st));
+      RS_TRY(fft_local_c2c(p, p->W2, D, nc, CUFFT_INVERSE, st));
     } else {
-      RS_TRY(exchange_backward(p, X, D, p->W2, nc, scale, st));
-      RS_TRY(fft_local(p, D, D, nc, CUFFT_INVERSE, st));
+      RS_TRY(exchange_backward(p, l, X, D, p->W2, nc, scale, st));
+      RS_TRY(fft_local_c2c(p, D, D, nc, CUFFT_INVERSE, st));
     }
   }
   return BRI17_OK;
@@ -648,41 +802,110 @@ int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev,
   if (u_dev == F_dev) return fail(BRI17_ERR_INVALID_ARG, "u_dev and F_dev must be distinct (F is scratch)");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
+  const Layout &l = p->lc;
   const double2 *u = static_cast<const double2 *>(u_dev);
   double2 *F = static_cast<double2 *>(F_dev);
   const int dim = p->dim;
-  int kb[3] = {0, p->k1_beg[p->rank], 0};
-  int ls[3] = {p->shape[0], p->n1_loc, p->shape[2]};
   p->timings_valid = false;
   mark(p, 0, st);
-  RS_TRY(fft_local(p, u, F, dim, CUFFT_FORWARD, st));                       // :57 (axes 1..)
+  RS_TRY(fft_local_c2c(p, u, F, dim, CUFFT_FORWARD, st));                   // :57 (axes 1..)
   mark(p, 1, st);
   double2 *X = F;  // Fourier-side block
   if (p->nranks > 1) {
     X = p->W;
-    RS_TRY(exchange_forward(p, F, p->W, p->W2, dim, st));
+    RS_TRY(exchange_forward(p, l, F, p->W, p->W2, dim, st));
   }
   mark(p, 2, st);
-  RS_TRY(fft_axis0(p, X, dim, CUFFT_FORWARD, st));                          // :57 (axis 0)
+  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_FORWARD, st));                       // :57 (axis 0)
   mark(p, 3, st);
-  if (p->fourier_count)                                                     // :58-92, scale :93-106
-    RS_TRY(bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st));
+  RS_TRY(modal_on_block(p, l, X, st));                                      // :58-92, scale :93-106
   mark(p, 4, st);
-  RS_TRY(fft_axis0(p, X, dim, CUFFT_INVERSE, st));                          // :95
+  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_INVERSE, st));                       // :95
   mark(p, 5, st);
   if (p->nranks > 1) {
     if (p->mode == 1) {
-      RS_TRY(exchange_backward(p, X, p->W2, nullptr, dim, 1.0, st));
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));
       mark(p, 6, st);
-      RS_TRY(fft_local(p, p->W2, F, dim, CUFFT_INVERSE, st));
+      RS_TRY(fft_local_c2c(p, p->W2, F, dim, CUFFT_INVERSE, st));
     } else {
-      RS_TRY(exchange_backward(p, X, F, p->W2, dim, 1.0, st));
+      RS_TRY(exchange_backward(p, l, X, F, p->W2, dim, 1.0, st));
       mark(p, 6, st);
-      RS_TRY(fft_local(p, F, F, dim, CUFFT_INVERSE, st));
+      RS_TRY(fft_local_c2c(p, F, F, dim, CUFFT_INVERSE, st));
     }
   } else {
     mark(p, 6, st);
-    RS_TRY(fft_local(p, F, F, dim, CUFFT_INVERSE, st));
+    RS_TRY(fft_local_c2c(p, F, F, dim, CUFFT_INVERSE, st));
+  }
+  mark(p, 7, st);
+  p->timings_valid = true;
+  return BRI17_OK;
+}
+
+// Real fields (plain doubles, [dim][n0_count][N1][(N2)]): r2c over the trailing axes, half
+// spectrum everywhere in between, c2r back.  Same operator as bri17_real_space_apply_f64
+// restricted to real input (what the reference always feeds it, tests/test_bri17.cpp:133-136).
+int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev, void *stream) {
+  if (!p || !u_dev || !F_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  DeviceGuard guard(p->device);
+  cudaStream_t st = cudaStream_t(stream);
+  Layout &l = p->lr;
+  if (!l.ready) RS_TRY(setup_layout(p, l));
+  const int dim = p->dim;
+  if (p->nranks == 1) RS_TRY(ensure_buffers(p, std::max<size_t>(sizeof(double2) * dim * l.t_count, 16)));
+  const double *u = static_cast<const double *>(u_dev);
+  double *F = static_cast<double *>(F_dev);
+  double2 *T = p->W2;  // local-transform layout [c][n0_loc][S1][S2e]
+  p->timings_valid = false;
+  mark(p, 0, st);
+  // cuFFT wants 16-byte aligned real arrays; component c starts at c*real_count doubles, which
+  // is misaligned when the slab holds an odd number of values: stage those through rbuf.
+  if ((p->real_count & 1) && !p->rbuf) BRI17_CUDA_TRY(cudaMalloc(&p->rbuf, sizeof(double) * (p->real_count + 2)));
+  auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; };
+  if (l.have_local) {
+    RS_CUFFT_TRY(cufftSetStream(l.fwd_local, st));
+    for (int c = 0; c < dim; c++) {
+      double *src = const_cast<double *>(u) + c * p->real_count;
+      if (misaligned(src)) {
+        BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
+        src = p->rbuf;
+      }
+      RS_CUFFT_TRY(cufftExecD2Z(l.fwd_local, src, (cufftDoubleComplex *)(T + c * l.t_count)));
+    }
+  }
+  mark(p, 1, st);
+  double2 *X = T;
+  if (p->nranks > 1) {
+    X = p->W;
+    double2 *S = p->W2 + p->real_upper;  // packed send pieces (NCCL mode)
+    RS_TRY(exchange_forward(p, l, T, p->W, S, dim, st));
+  }
+  mark(p, 2, st);
+  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_FORWARD, st));
+  mark(p, 3, st);
+  RS_TRY(modal_on_block(p, l, X, st));
+  mark(p, 4, st);
+  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_INVERSE, st));
+  mark(p, 5, st);
+  double2 *D = T;
+  if (p->nranks > 1) {
+    if (p->mode == 1) {
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));   // peers store into our W2
+    } else {
+      double2 *R = p->W2 + p->real_upper;                                 // packed receive pieces
+      RS_TRY(exchange_backward(p, l, X, p->W2, R, dim, 1.0, st));
+    }
+    D = p->W2;
+  }
+  mark(p, 6, st);
+  if (l.have_local) {
+    RS_CUFFT_TRY(cufftSetStream(l.inv_local, st));
+    for (int c = 0; c < dim; c++) {
+      double *dst = F + c * p->real_count;
+      double *out = misaligned(dst) ? p->rbuf : dst;
+      RS_CUFFT_TRY(cufftExecZ2D(l.inv_local, (cufftDoubleComplex *)(D + c * l.t_count), out));
+      if (out != dst)
+        BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
+    }
   }
   mark(p, 7, st);
   p->timings_valid = true;
@@ -708,62 +931,22 @@ int bri17_cg_solve_f64(bri17_rs_plan *p, const void *b_dev, void *x_dev, double 
   if (max_iter < 0) return fail(BRI17_ERR_INVALID_ARG, "max_iter < 0");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
+  const long long n = 2LL * p->dim * p->real_count;  // interleaved complex -> doubles
+  return cg_core(p, [&](const double *d, double *Ad) { return bri17_real_space_apply_f64(p, d, Ad, st); },
+                 static_cast<const double *>(b_dev), static_cast<double *>(x_dev), n, rtol, max_iter,
+                 check_every, iterations, rel_residual, st);
+}
+
+int bri17_cg_solve_real_f64(bri17_rs_plan *p, const void *b_dev, void *x_dev, double rtol, int max_iter,
+                            int check_every, int *iterations, double *rel_residual, void *stream) {
+  if (!p || !b_dev || !x_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  if (max_iter < 0) return fail(BRI17_ERR_INVALID_ARG, "max_iter < 0");
+  DeviceGuard guard(p->device);
+  cudaStream_t st = cudaStream_t(stream);
   const long long n = (long long)p->dim * p->real_count;
-  const size_t bytes = sizeof(double2) * std::max<long long>(n, 1);
-  if (!p->cg_r) {
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_r, bytes));
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_p, bytes));
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_Ap, bytes));
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_partial, sizeof(double) * RED_CTAS));
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_scalars, sizeof(double) * 8));
-  }
-  const double2 *b = static_cast<const double2 *>(b_dev);
-  double2 *x = static_cast<double2 *>(x_dev), *r = p->cg_r, *d = p->cg_p, *Ad = p->cg_Ap;
-  double *sc = p->cg_scalars;  // [0] rr (even iter) [1] rr (odd iter) [2] pAp [3] bb
-  auto reduce_to = [&](double *slot) -> int {
-    cg_finish_kernel<<<1, RED_THREADS, 0, st>>>(p->cg_partial, RED_CTAS, slot);
-    if (p->nranks > 1) RS_NCCL_TRY(ncclAllReduce(slot, slot, 1, ncclDouble, ncclSum, p->comm, st));
-    return BRI17_OK;
-  };
-  // x = 0, r = b, d = r, rr = <r,r>
-  BRI17_CUDA_TRY(cudaMemsetAsync(x, 0, bytes, st));
-  BRI17_CUDA_TRY(cudaMemcpyAsync(r, b, bytes, cudaMemcpyDeviceToDevice, st));
-  BRI17_CUDA_TRY(cudaMemcpyAsync(d, b, bytes, cudaMemcpyDeviceToDevice, st));
-  cg_dot_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(r, r, n, p->cg_partial);
-  RS_TRY(reduce_to(sc + 0));
-  BRI17_CUDA_TRY(cudaMemcpyAsync(sc + 3, sc + 0, sizeof(double), cudaMemcpyDeviceToDevice, st));
-  double h[4] = {0, 0, 0, 0};
-  BRI17_CUDA_TRY(cudaMemcpyAsync(h, sc, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
-  BRI17_CUDA_TRY(cudaStreamSynchronize(st));
-  const double bb = h[3];
-  int it = 0;
-  double rr_host = bb;
-  if (bb > 0.) {
-    for (; it < max_iter;) {
-      double *rr = sc + (it & 1), *rr_new = sc + ((it + 1) & 1);
-      RS_TRY(bri17_real_space_apply_f64(p, d, Ad, st));
-      cg_dot_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(d, Ad, n, p->cg_partial);
-      RS_TRY(reduce_to(sc + 2));
-      cg_update_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(x, r, d, Ad, n, rr, sc + 2, p->cg_partial);
-      RS_TRY(reduce_to(rr_new));
-      cg_direction_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(d, r, n, rr_new, rr);
-      it++;
-      if (check_every > 0 && (it % check_every == 0 || it == max_iter)) {
-        BRI17_CUDA_TRY(cudaMemcpyAsync(&rr_host, rr_new, sizeof(double), cudaMemcpyDeviceToHost, st));
-        BRI17_CUDA_TRY(cudaStreamSynchronize(st));
-        if (rr_host <= rtol * rtol * bb) break;
-      }
-    }
-    if (check_every <= 0) {
-      BRI17_CUDA_TRY(cudaMemcpyAsync(&rr_host, sc + (it & 1), sizeof(double), cudaMemcpyDeviceToHost, st));
-      BRI17_CUDA_TRY(cudaStreamSynchronize(st));
-    }
-  }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(BRI17_ERR_CUDA, std::string("CG: ") + cudaGetErrorString(e));
-  if (iterations) *iterations = it;
-  if (rel_residual) *rel_residual = bb > 0. ? std::sqrt(rr_host / bb) : 0.;
-  return BRI17_OK;
+  return cg_core(p, [&](const double *d, double *Ad) { return bri17_real_space_apply_real_f64(p, d, Ad, st); },
+                 static_cast<const double *>(b_dev), static_cast<double *>(x_dev), n, rtol, max_iter,
+                 check_every, iterations, rel_residual, st);
 }
 
 }  // extern "C"

@@ -47,7 +47,8 @@ class RealSpaceOperator:
         self.n0_begin, self.n0_count, self.k1_begin, self.k1_count = (x.value for x in v)
         self.real_shape = (self.dim, self.n0_count) + self.shape[1:]
         self.fourier_shape = (self.dim, self.shape[0], self.k1_count) + self.shape[2:]
-        self.exchange_bytes = int(self._lib.bri17_rs_plan_exchange_bytes(self._plan))
+        self.exchange_bytes = int(self._lib.bri17_rs_plan_exchange_bytes(self._plan, 0))
+        self.exchange_bytes_real = int(self._lib.bri17_rs_plan_exchange_bytes(self._plan, 1))
 
     @classmethod
     def from_process_group(cls, shape, L, mu, nu, device, exchange_mode=EXCHANGE_NCCL):
@@ -88,6 +89,30 @@ class RealSpaceOperator:
         check(self._lib.bri17_real_space_apply_f64(self._plan, _dev_ptr(u), _dev_ptr(out),
                                                    _stream_ptr(stream)))
         return out
+
+    def apply_real(self, u, out=None, stream=None):
+        """Same operator on a REAL field, float64 ``(dim, n0_count, N1[, N2])``: r2c
+        half-spectrum path (half the FFT, exchange and modal work)."""
+        import torch
+        if tuple(u.shape) != tuple(self.real_shape) or u.dtype != torch.float64:
+            raise ValueError(f"u: expected float64 {self.real_shape}")
+        if out is None:
+            out = torch.empty_like(u)
+        check(self._lib.bri17_real_space_apply_real_f64(self._plan, _dev_ptr(u), _dev_ptr(out),
+                                                        _stream_ptr(stream)))
+        return out
+
+    def cg_solve_real(self, b, rtol=1e-8, max_iter=1000, check_every=10, stream=None):
+        """CG on real float64 fields (see cg_solve)."""
+        import torch
+        if tuple(b.shape) != tuple(self.real_shape) or b.dtype != torch.float64:
+            raise ValueError(f"b: expected float64 {self.real_shape}")
+        x = torch.empty_like(b)
+        it, res = C.c_int(), C.c_double()
+        check(self._lib.bri17_cg_solve_real_f64(self._plan, _dev_ptr(b), _dev_ptr(x), float(rtol),
+                                                int(max_iter), int(check_every), C.byref(it),
+                                                C.byref(res), _stream_ptr(stream)))
+        return x, it.value, res.value
 
     def forward_fft(self, x, stream=None):
         """DFT (sign -1, unnormalised) of a real-space slab -> Fourier-space slab."""

@@ -74,6 +74,16 @@ BRI17_API int64_t bri17_rs_plan_fourier_count(const bri17_rs_plan *plan);
 BRI17_API int bri17_real_space_apply_f64(bri17_rs_plan *plan, const void *u_dev, void *F_dev,
                                          void *stream);
 
+/*
+ * Same operator for REAL fields stored as plain doubles, [dim][n0_count][N1][(N2)]
+ * (the reference only ever applies compute_Ku to real data carried as complex,
+ * tests/test_bri17.cpp:133-136).  r2c over the trailing axes keeps the
+ * non-redundant half spectrum of the last axis (K^(N-k) = K^(k)): half the FFT
+ * work, half the all-to-all bytes, half the modal traffic.  u_dev is preserved.
+ */
+BRI17_API int bri17_real_space_apply_real_f64(bri17_rs_plan *plan, const void *u_dev, void *F_dev,
+                                              void *stream);
+
 /* The two halves, exposed for callers that work in Fourier space:
  * forward: x_dev (real-space slab, preserved) -> x_hat_dev (Fourier slab
  *          [dim][N0][k1_count][(N2)]), unnormalised, sign -1 (theory.rst:60);
@@ -92,8 +102,9 @@ BRI17_API bri17_plan *bri17_rs_plan_modal(bri17_rs_plan *plan);
  * all), [2] axis-0 forward FFT, [3] modal apply, [4] axis-0 inverse FFT,
  * [5] backward exchange, [6] local inverse FFT, [7] total.  n <= 8. */
 BRI17_API int bri17_rs_plan_last_timings(bri17_rs_plan *plan, double *ms, int n);
-/* Bytes this rank sent to other ranks in one exchange (one direction). */
-BRI17_API int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *plan);
+/* Bytes this rank sends to other ranks in one exchange (one direction), for the
+ * complex (real_layout = 0) or the half-spectrum (real_layout = 1) path. */
+BRI17_API int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *plan, int real_layout);
 
 /*
  * Matrix-free conjugate gradients on  A x = b,  A = the real-space operator
@@ -108,6 +119,11 @@ BRI17_API int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *plan);
 BRI17_API int bri17_cg_solve_f64(bri17_rs_plan *plan, const void *b_dev, void *x_dev, double rtol,
                                  int max_iter, int check_every, int *iterations,
                                  double *rel_residual, void *stream);
+
+/* Same on real fields (plain doubles) through bri17_real_space_apply_real_f64. */
+BRI17_API int bri17_cg_solve_real_f64(bri17_rs_plan *plan, const void *b_dev, void *x_dev, double rtol,
+                                      int max_iter, int check_every, int *iterations,
+                                      double *rel_residual, void *stream);
 
 #ifdef __cplusplus
 }

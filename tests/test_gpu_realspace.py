@@ -61,6 +61,53 @@ def test_real_space_apply_vs_numpy_restatement(oracle_mod, shape):
     assert t["total"] > 0 and set(t) >= {"modal", "exchange_fwd"}
 
 
+@pytest.mark.parametrize("shape", [(16, 12, 10), (64, 64), (5, 7), (8, 8, 33), (9, 6, 7), (32, 32, 32)])
+def test_real_half_spectrum_path_vs_numpy_restatement(oracle_mod, shape):
+    """r2c / c2r path on real float64 fields against the
+    c2c restatement of the reference harness: same operator, half the work."""
+    dim = len(shape)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(43)
+    u = rng.standard_normal((dim,) + shape)
+    ref = real_space_apply_ref(oracle_mod.best(), shape, L, MU, NU, u + 0j).real
+    op = RealSpaceOperator(shape, L, MU, NU)
+    ud = torch.from_numpy(u).cuda()
+    F = op.apply_real(ud).cpu().numpy()
+    assert np.abs(F - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert torch.equal(ud.cpu(), torch.from_numpy(u))                 # input preserved
+    Fc = op.apply(torch.from_numpy(u + 0j).cuda()).cpu().numpy()      # and the c2c path agrees
+    assert np.abs(F - Fc.real).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_kat_through_real_path(dim):
+    """The reference's dense-matrix known-answer tests through the r2c path."""
+    E = kat.load_elements()
+    shape, L = kat.SHAPE[dim], kat.grid_L(dim)
+    op = RealSpaceOperator(shape, L, kat.MU, kat.NU)
+    size = int(np.prod(shape))
+    K = np.zeros((size * dim, size * dim))
+    u = torch.zeros((dim,) + shape, dtype=torch.float64, device="cuda")
+    for j in range(size * dim):
+        u.view(-1)[j] = 1.0
+        K[:, j] = op.apply_real(u).cpu().numpy().ravel()
+        u.view(-1)[j] = 0.0
+    kat.assert_equal(kat.assemble_expected_stiffness(shape, E[f"Ke{dim}"]), K)
+
+
+def test_cg_real_path(oracle_mod):
+    shape = (16, 12, 10)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(5)
+    x_true = rng.standard_normal((3,) + shape)
+    x_true -= x_true.mean(axis=(1, 2, 3), keepdims=True)
+    b = real_space_apply_ref(oracle_mod.best(), shape, L, MU, NU, x_true + 0j).real
+    op = RealSpaceOperator(shape, L, MU, NU)
+    x, iters, res = op.cg_solve_real(torch.from_numpy(np.ascontiguousarray(b)).cuda(), rtol=1e-11,
+                                     max_iter=2000, check_every=5)
+    assert res <= 1e-11 and np.abs(x.cpu().numpy() - x_true).max() <= 1e-7 * np.abs(x_true).max()
+
+
 def test_forward_inverse_fft_conventions():
     """theory.rst:60 (sign -1, unnormalised) and :72 (1/|N| on the inverse)."""
     shape = (12, 10, 9)
