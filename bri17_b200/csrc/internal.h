@@ -99,6 +99,8 @@ struct bri17_plan {
   int max_smem_optin = 0;
   bri17b200::AxisTables tab[3];
   int apply_variant = -1;  // -1: default
+  int mapping = 0;         // 0 auto, 1 always row tiles, 2 always flat tiles
+  int last_flat = 0;
   int64_t host_chunk_rows = 0;
   int host_streams = 3;
   // staging for the host-buffer path (lazily allocated, owned by the plan)

@@ -23,6 +23,7 @@
 //  * Arithmetic uses __dmul_rn/__dadd_rn in the reference's written order, so
 //    no multiply-add is contracted and the result is bit-identical to the
 //    reference compiled without FMA (the oracle's parity build).
+#include <algorithm>
 #include <cstdio>
 
 #include "internal.h"
@@ -252,6 +253,162 @@ __global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_kernel(co
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// K1f / K2f: "flat" modal stiffness apply for rows that do not fill whole tiles
+// (fastest extent such as 513 = N/2+1 of a half spectrum, 300, 5, ...).  A tile
+// is THREADS*VEC consecutive elements of the row-major block, rows concatenated,
+// so no lane is idle except in the very last tile; each element derives its
+// (a, b, col) by two integer divisions and reads its nine factors from the
+// shared-memory tables of all three axes.  Same arithmetic, same results.
+// ---------------------------------------------------------------------------
+struct FlatIndex {
+  long long i;
+  int a, b, col;
+};
+__device__ __forceinline__ FlatIndex flat_index(const TileGeom &g, long long i) {
+  FlatIndex f;
+  f.i = i;
+  if (g.n_tiles <= 0x7fffffffLL / 1 && g.n_rows * g.n_inner <= 0x7fffffffLL) {  // 32-bit fast path
+    const unsigned iu = unsigned(i), row = iu / unsigned(g.n_inner);
+    f.col = int(iu - row * unsigned(g.n_inner));
+    f.a = int(row / unsigned(g.n_mid));
+    f.b = int(row - unsigned(f.a) * unsigned(g.n_mid));
+  } else {
+    const long long row = i / g.n_inner;
+    f.col = int(i - row * g.n_inner);
+    f.a = int(row / g.n_mid);
+    f.b = int(row - (long long)f.a * g.n_mid);
+  }
+  return f;
+}
+
+template <int DIM, int THREADS, int VEC, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_flat_kernel(const ApplyParams p) {
+  extern __shared__ double smem[];
+  constexpr int TILE = THREADS * VEC;
+  const TileGeom &g = p.g;
+  // tables of the local ranges: outer | mid | inner, each [phi|chi|psi]
+  const double *tO, *tM, *tI;
+  int sO, sM, sI, oO, oM, oI;
+  if (p.stage_outer) {
+    const int no = g.n_outer, nm = DIM == 3 ? g.n_mid : 0, ni = g.n_inner;
+    for (int x = threadIdx.x; x < 3 * no; x += THREADS) {
+      const int w = x / no, kk = x - w * no;
+      smem[x] = p.tab_outer[size_t(w) * p.N_outer + g.kb_outer + kk];
+    }
+    if constexpr (DIM == 3)
+      for (int x = threadIdx.x; x < 3 * nm; x += THREADS) {
+        const int w = x / nm, kk = x - w * nm;
+        smem[3 * no + x] = p.tab_mid[size_t(w) * p.N_mid + g.kb_mid + kk];
+      }
+    for (int x = threadIdx.x; x < 3 * ni; x += THREADS) {
+      const int w = x / ni, kk = x - w * ni;
+      smem[3 * (no + nm) + x] = p.tab_inner[size_t(w) * p.N_inner + g.kb_inner + kk];
+    }
+    __syncthreads();
+    tO = smem; sO = no; oO = 0;
+    tM = smem + 3 * no; sM = nm; oM = 0;
+    tI = smem + 3 * (no + nm); sI = ni; oI = 0;
+  } else {
+    tO = p.tab_outer; sO = p.N_outer; oO = g.kb_outer;
+    tM = p.tab_mid; sM = p.N_mid; oM = g.kb_mid;
+    tI = p.tab_inner; sI = p.N_inner; oI = g.kb_inner;
+  }
+  const double mu = p.mu, scaling = p.scaling;
+  const bool scale_out = p.out_scale != 1.0;
+  const long long total = g.n_rows * g.n_inner;
+
+  for (long long tile = blockIdx.x; tile * TILE < total; tile += gridDim.x) {
+    FlatIndex f[VEC];
+    bool ok[VEC];
+    double2 u[VEC][DIM];
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      const long long i = tile * TILE + j * THREADS + threadIdx.x;
+      ok[j] = i < total;
+      f[j] = flat_index(g, ok[j] ? i : 0);
+#pragma unroll
+      for (int c = 0; c < DIM; c++)
+        if (ok[j]) u[j][c] = __ldcs(p.u + c * p.u_stride + i);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      if (!ok[j]) continue;
+      const int ia = oO + f[j].a, ii = oI + f[j].col;
+      const double p0 = tO[ia], c0 = tO[sO + ia], s0 = tO[2 * sO + ia];
+      const double pI = tI[ii], cI = tI[sI + ii], sIv = tI[2 * sI + ii];
+      double2 *o = p.f + f[j].i;
+      if constexpr (DIM == 3) {
+        const int ib = oM + f[j].b;
+        const double p1 = tM[ib], c1 = tM[sM + ib], s1 = tM[2 * sM + ib];
+        const double H00 = mul(mul(p0, c1), cI);                 // bri17.hpp:276
+        const double H11 = mul(mul(c0, p1), cI);                 // :277
+        const double H22 = mul(mul(c0, c1), pI);                 // :278
+        const double Kd = mul(mu, add(add(H00, H11), H22));      // :279
+        const double K00 = add(mul(scaling, H00), Kd);           // :280
+        const double K11 = add(mul(scaling, H11), Kd);           // :284
+        const double K22 = add(mul(scaling, H22), Kd);           // :288
+        const double K01 = mul(mul(mul(scaling, s0), s1), cI);   // :281
+        const double K02 = mul(mul(mul(scaling, s0), c1), sIv);  // :282
+        const double K12 = mul(mul(mul(scaling, c0), s1), sIv);  // :285
+        const double2 u0 = u[j][0], u1 = u[j][1], u2 = u[j][2];
+        double2 f0, f1, f2;
+        f0.x = add(add(mul(K00, u0.x), mul(K01, u1.x)), mul(K02, u2.x));
+        f0.y = add(add(mul(K00, u0.y), mul(K01, u1.y)), mul(K02, u2.y));
+        f1.x = add(add(mul(K01, u0.x), mul(K11, u1.x)), mul(K12, u2.x));
+        f1.y = add(add(mul(K01, u0.y), mul(K11, u1.y)), mul(K12, u2.y));
+        f2.x = add(add(mul(K02, u0.x), mul(K12, u1.x)), mul(K22, u2.x));
+        f2.y = add(add(mul(K02, u0.y), mul(K12, u1.y)), mul(K22, u2.y));
+        if (scale_out) {
+          f0.x = mul(f0.x, p.out_scale); f0.y = mul(f0.y, p.out_scale);
+          f1.x = mul(f1.x, p.out_scale); f1.y = mul(f1.y, p.out_scale);
+          f2.x = mul(f2.x, p.out_scale); f2.y = mul(f2.y, p.out_scale);
+        }
+        __stcs(o, f0);
+        __stcs(o + p.f_stride, f1);
+        __stcs(o + 2 * p.f_stride, f2);
+      } else {
+        const double H00 = mul(p0, cI);                          // :268
+        const double H11 = mul(c0, pI);                          // :269
+        const double Kd = mul(mu, add(H00, H11));                // :270
+        const double K00 = add(mul(scaling, H00), Kd);           // :271
+        const double K01 = mul(mul(scaling, s0), sIv);           // :272
+        const double K11 = add(mul(scaling, H11), Kd);           // :274
+        const double2 u0 = u[j][0], u1 = u[j][1];
+        double2 f0, f1;
+        f0.x = add(mul(K00, u0.x), mul(K01, u1.x));
+        f0.y = add(mul(K00, u0.y), mul(K01, u1.y));
+        f1.x = add(mul(K01, u0.x), mul(K11, u1.x));
+        f1.y = add(mul(K01, u0.y), mul(K11, u1.y));
+        if (scale_out) {
+          f0.x = mul(f0.x, p.out_scale); f0.y = mul(f0.y, p.out_scale);
+          f1.x = mul(f1.x, p.out_scale); f1.y = mul(f1.y, p.out_scale);
+        }
+        __stcs(o, f0);
+        __stcs(o + p.f_stride, f1);
+      }
+    }
+  }
+}
+
+// K6, flat mapping
+template <int DIM>
+__global__ void __launch_bounds__(256) freq_index_map_flat_kernel(const TileGeom g, int32_t *k_out) {
+  constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
+  const long long total = g.n_rows * g.n_inner;
+  for (long long tile = blockIdx.x; tile * TILE < total; tile += gridDim.x)
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      const long long i = tile * TILE + j * THREADS + threadIdx.x;
+      if (i >= total) continue;
+      const FlatIndex f = flat_index(g, i);
+      int32_t *o = k_out + i * DIM;
+      o[0] = g.kb_outer + f.a;
+      if constexpr (DIM == 3) { o[1] = g.kb_mid + f.b; o[2] = g.kb_inner + f.col; }
+      else o[1] = g.kb_inner + f.col;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -646,10 +803,50 @@ static int check_launch(const char *what) {
   return BRI17_OK;
 }
 
+// Row tiling pads every row to a multiple of the tile; beyond a few per cent of idle
+// lanes the flat mapping is used instead.
+static bool rows_fill_tiles(const Block &b, int tile) {
+  const int n_inner = b.n[b.dim - 1];
+  const long long padded = (long long)((n_inner + tile - 1) / tile) * tile;
+  return padded * 100 <= (long long)n_inner * 103;
+}
+
+static int launch_apply_flat(bri17_plan *p, const Block &b, ApplyParams &ap, cudaStream_t stream) {
+  constexpr int THREADS = 256, VEC = 2;
+  void (*kern)(const ApplyParams) = b.dim == 3 ? modal_stiffness_apply_flat_kernel<3, THREADS, VEC, 2>
+                                                : modal_stiffness_apply_flat_kernel<2, THREADS, VEC, 2>;
+  const int n_mid = b.dim == 3 ? b.n[1] : 0;
+  size_t smem = size_t(3) * (size_t(b.n[0]) + n_mid + b.n[b.dim - 1]) * sizeof(double);
+  if (smem <= 48 * 1024) ap.stage_outer = 1; else { smem = 0; ap.stage_outer = 0; }
+  int occ = 0;
+  BRI17_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  if (occ < 1) return fail(BRI17_ERR_CUDA, "flat apply kernel does not fit on an SM");
+  make_geom(b, THREADS * VEC, p->sm_count * occ, &ap.g);
+  const long long tiles = (b.modes + THREADS * VEC - 1) / (THREADS * VEC);
+  const int grid = int(std::min<long long>(tiles, (long long)p->sm_count * occ));
+  kern<<<grid, THREADS, smem, stream>>>(ap);
+  p->last_grid = grid; p->last_block = THREADS; p->last_smem = int64_t(smem);
+  p->last_flat = 1;
+  p->launches++;
+  return check_launch("modal_stiffness_apply_flat");
+}
+
 int launch_apply(bri17_plan *p, const Block &b, const void *u, void *f, int64_t u_stride,
                  int64_t f_stride, double out_scale, cudaStream_t stream) {
   const int vi = p->apply_variant < 0 ? default_variant(p) : p->apply_variant;
   const Variant &v = kVariants[vi];
+  const bool flat = p->mapping == 2 || (p->mapping == 0 && !rows_fill_tiles(b, v.threads * v.vec));
+  if (flat) {
+    ApplyParams fp;
+    fill_params(p, b, &fp);
+    fp.u = static_cast<const double2 *>(u);
+    fp.f = static_cast<double2 *>(f);
+    fp.u_stride = u_stride;
+    fp.f_stride = f_stride;
+    fp.out_scale = out_scale;
+    return launch_apply_flat(p, b, fp, stream);
+  }
+  p->last_flat = 0;
   ApplyKernel kern = b.dim == 3 ? apply_kernel_for<3>(vi) : apply_kernel_for<2>(vi);
   if (!kern) return fail(BRI17_ERR_UNSUPPORTED, "unknown apply variant");
 
@@ -680,7 +877,14 @@ int launch_apply(bri17_plan *p, const Block &b, const void *u, void *f, int64_t 
 int launch_index_map(bri17_plan *p, const Block &b, int32_t *k_out, cudaStream_t stream) {
   TileGeom g;
   const int grid = make_geom(b, 512, p->sm_count * 8, &g);
-  if (b.dim == 3) freq_index_map_kernel<3><<<grid, 256, 0, stream>>>(g, k_out);
+  // same choice of mapping as the apply kernels, so that this exposes what they derive
+  const bool flat = p->mapping == 2 || (p->mapping == 0 && !rows_fill_tiles(b, 512));
+  if (flat) {
+    const long long tiles = (b.modes + 511) / 512;
+    const int fgrid = int(std::min<long long>(tiles, (long long)p->sm_count * 8));
+    if (b.dim == 3) freq_index_map_flat_kernel<3><<<fgrid, 256, 0, stream>>>(g, k_out);
+    else freq_index_map_flat_kernel<2><<<fgrid, 256, 0, stream>>>(g, k_out);
+  } else if (b.dim == 3) freq_index_map_kernel<3><<<grid, 256, 0, stream>>>(g, k_out);
   else freq_index_map_kernel<2><<<grid, 256, 0, stream>>>(g, k_out);
   p->launches++;
   return check_launch("freq_index_map");

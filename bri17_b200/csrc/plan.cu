@@ -178,6 +178,9 @@ int bri17_plan_set_option(bri17_plan *p, const char *key, int64_t value) {
     if (value < -1 || value >= num_variants())
       return fail(BRI17_ERR_INVALID_ARG, "apply_variant out of range");
     p->apply_variant = int(value);
+  } else if (!std::strcmp(key, "mapping")) {
+    if (value < 0 || value > 2) return fail(BRI17_ERR_INVALID_ARG, "mapping must be 0 (auto), 1 (rows) or 2 (flat)");
+    p->mapping = int(value);
   } else if (!std::strcmp(key, "host_chunk_rows")) {
     if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "host_chunk_rows < 0");
     p->host_chunk_rows = value;
@@ -201,6 +204,7 @@ int bri17_plan_get_info(const bri17_plan *p, const char *key, int64_t *value) {
   else if (!std::strcmp(key, "last_block")) *value = p->last_block;
   else if (!std::strcmp(key, "last_smem")) *value = p->last_smem;
   else if (!std::strcmp(key, "launches")) *value = p->launches;
+  else if (!std::strcmp(key, "last_flat")) *value = p->last_flat;
   else if (!std::strcmp(key, "device")) *value = p->device;
   else if (!std::strcmp(key, "table_bytes")) {
     int64_t b = 0;

@@ -51,4 +51,21 @@ ms = timed(lambda: op.modal_strain_displacement_field(slab, (100, 0, 0)), 10)
 out["strain_field_64planes"] = {"ms": ms, "bytes_per_mode": 48, "gbs": 48 * 64 * edge * edge / ms / 1e6}
 ms = timed(lambda: op.freq_index_map(slab, (100, 0, 0)), 10)
 out["index_map_64planes"] = {"ms": ms, "bytes_per_mode": 12, "gbs": 12 * 64 * edge * edge / ms / 1e6}
+# ragged fastest axis: the 513-wide half spectrum of a 1024^3 r2c block, row tiles vs flat tiles
+del u
+rag = (256, 256, 513)
+opr = b.ModalOperator((256, 256, 1024), (1.0, 1.0, 1.0), 5.6, 0.3)
+ur = torch.view_as_complex(torch.randn((3,) + rag + (2,), dtype=torch.float64, device="cuda"))
+fr = torch.empty_like(ur)
+for name, mapping in (("rows", 1), ("flat", 2)):
+    opr.set_option("mapping", mapping)
+    ms = timed(lambda: opr.apply_modal_stiffness(ur, out=fr))
+    out[f"apply_256x256x513_{name}"] = {"ms": ms, "gbs": 96 * ur[0].numel() / ms / 1e6}
+opf = b.ModalOperator(shape, L, 5.6, 0.3)
+uf = torch.view_as_complex(torch.randn((3,) + shape + (2,), dtype=torch.float64, device="cuda"))
+ff = torch.empty_like(uf)
+for name, mapping in (("rows", 1), ("flat", 2)):
+    opf.set_option("mapping", mapping)
+    ms = timed(lambda: opf.apply_modal_stiffness(uf, out=ff))
+    out[f"apply_512^3_{name}"] = {"ms": ms, "gbs": 96 * M / ms / 1e6}
 print(json.dumps(out))

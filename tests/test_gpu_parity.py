@@ -84,6 +84,32 @@ def test_apply_matches_oracle(oracle_mod, shape):
     assert np.array_equal(f, ref), "expected bit-identical output (unfused fp64, host tables)"
 
 
+@pytest.mark.parametrize("mapping", [1, 2])
+@pytest.mark.parametrize("shape", SHAPES + [(6, 5, 513), (3, 257), (7, 3, 300)])
+def test_row_and_flat_mappings_match_oracle(oracle_mod, shape, mapping):
+    """Both tile mappings (row tiles with register-cached columns; flat tiles for
+    ragged rows such as a 513-wide half spectrum) on every shape: same bits, and
+    the index map exposes the mapping in use."""
+    dim = len(shape)
+    L = spacing_L(shape)
+    u = oracle_mod.synthetic_u_hat(dim, shape, seed=123)
+    ref = oracle_mod.best().apply_modal_stiffness(shape, L, MU, NU, u)
+    op = b.ModalOperator(shape, L, MU, NU)
+    op.set_option("mapping", mapping)
+    f = op.apply_modal_stiffness(to_dev(u)).cpu().numpy()
+    assert op.info("last_flat") == (mapping == 2)
+    assert np.array_equal(f, ref)
+    k = op.freq_index_map().cpu().numpy()
+    assert np.array_equal(k, oracle_mod.freq_index_map((0,) * dim, shape))
+    # a slab with offsets on every axis
+    if all(n >= 2 for n in shape):
+        kb = tuple(n // 2 for n in shape)
+        local = tuple(n - n // 2 for n in shape)
+        sl = (slice(None),) + tuple(slice(a, a + n) for a, n in zip(kb, local))
+        fs = op.apply_modal_stiffness(to_dev(u[sl]), k_begin=kb).cpu().numpy()
+        assert np.array_equal(fs, ref[sl])
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_every_kernel_variant_matches_oracle(oracle_mod, dim):
     shape = (6, 1100) if dim == 2 else (6, 5, 1100)
@@ -92,6 +118,7 @@ def test_every_kernel_variant_matches_oracle(oracle_mod, dim):
     ref = oracle_mod.best().apply_modal_stiffness(shape, L, MU, NU, u)
     op = b.ModalOperator(shape, L, MU, NU)
     ud = to_dev(u)
+    op.set_option("mapping", 1)        # the variants are row-tile kernels
     for v in range(op.info("num_variants")):
         op.set_option("apply_variant", v)
         out = torch.full_like(ud, float("nan"))
