@@ -24,7 +24,7 @@ void free_host_stages(bri17_plan *p) {
 }
 
 static int ensure_stages(bri17_plan *p, int64_t bytes) {
-  if (int(p->stages.size()) == p->host_streams && p->stage_bytes >= bytes) return BRI17_OK;
+  if (int(p->stages.size()) == p->host_streams && p->stage_bytes >= bytes && p->stages[0].in) return BRI17_OK;
   free_host_stages(p);
   p->stages.resize(p->host_streams);
   for (auto &s : p->stages) {
@@ -36,9 +36,41 @@ static int ensure_stages(bri17_plan *p, int64_t bytes) {
   return BRI17_OK;
 }
 
+// Zero-copy variant (option "host_zero_copy"): when both buffers are page-locked and mapped,
+// the apply kernel reads u^ and writes f^ directly in host memory over PCIe, one launch, no
+// staging buffers.  Kept as an option: measured against the chunked pipeline in
+// profiles/r01_measurements.md.
+static int apply_host_zero_copy(bri17_plan *p, const Block &b, const void *u_host, void *f_host,
+                                int64_t comp_stride, double out_scale, bool *done) {
+  *done = false;
+  cudaPointerAttributes au{}, af{};
+  if (cudaPointerGetAttributes(&au, u_host) != cudaSuccess ||
+      cudaPointerGetAttributes(&af, f_host) != cudaSuccess) {
+    cudaGetLastError();
+    return BRI17_OK;
+  }
+  if (au.type != cudaMemoryTypeHost || af.type != cudaMemoryTypeHost || !au.devicePointer || !af.devicePointer)
+    return BRI17_OK;  // pageable memory: use the staged pipeline
+  if (p->stages.empty()) {
+    p->stages.resize(1);
+    BRI17_CUDA_TRY(cudaStreamCreateWithFlags(&p->stages[0].stream, cudaStreamNonBlocking));
+  }
+  cudaStream_t st = p->stages[0].stream;
+  int rc = launch_apply(p, b, au.devicePointer, af.devicePointer, comp_stride, comp_stride, out_scale, st);
+  if (rc) return rc;
+  BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+  *done = true;
+  return BRI17_OK;
+}
+
 int apply_host(bri17_plan *p, const Block &b, const void *u_host, void *f_host,
                int64_t comp_stride, double out_scale) {
   const int dim = b.dim;
+  if (p->host_zero_copy) {
+    bool done = false;
+    int zrc = apply_host_zero_copy(p, b, u_host, f_host, comp_stride, out_scale, &done);
+    if (zrc || done) return zrc;
+  }
   const int64_t plane = b.modes / b.n[0];  // modes per index of the slowest axis
   int64_t rows = p->host_chunk_rows;
   if (rows <= 0) {  // default: ~32 MiB per component per chunk

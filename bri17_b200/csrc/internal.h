@@ -103,6 +103,7 @@ struct bri17_plan {
   int last_flat = 0;
   int64_t host_chunk_rows = 0;
   int host_streams = 3;
+  int host_zero_copy = 0;  // 1: kernels access pinned host memory directly (no staging)
   // staging for the host-buffer path (lazily allocated, owned by the plan)
   struct HostStage {
     cudaStream_t stream = nullptr;

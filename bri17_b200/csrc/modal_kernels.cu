@@ -632,74 +632,87 @@ __device__ __forceinline__ AxisFactors axis_factors(const double *tab, int N, in
   return f;
 }
 
-template <int DIM, int MODE>
+template <int DIM, int MODE, int VEC>
 __global__ void __launch_bounds__(256, 2) modal_solve_kernel(const ApplyParams p) {
-  constexpr int THREADS = 256, TILE = THREADS;
+  constexpr int THREADS = 256, TILE = THREADS * VEC;
   constexpr int NIN = MODE == 0 ? DIM : DIM * (DIM + 1) / 2;
   constexpr int NOUT = MODE == 2 ? DIM * (DIM + 1) / 2 : DIM;
   const TileGeom &g = p.g;
   TileCursor cur;
-  int cached_chunk = -1, col = 0;
-  bool ok = false;
-  AxisFactors fI{};
+  int cached_chunk = -1;
+  int col[VEC];
+  bool ok[VEC];
+  AxisFactors fI[VEC];
   for (cur.init(g); cur.valid(g); cur.next(g)) {
     if (cur.chunk != cached_chunk) {
       cached_chunk = cur.chunk;
-      col = cur.chunk * TILE + threadIdx.x;
-      ok = col < g.n_inner;
-      fI = axis_factors(p.tab_inner, p.N_inner, g.kb_inner + (ok ? col : 0));
-    }
-    if (!ok) continue;
-    const long long i = cur.row * g.n_inner + col;
-    Cplx in[NIN];
 #pragma unroll
-    for (int s = 0; s < NIN; s++) {
-      const double2 v = __ldcs(p.u + i * p.u_mstride + s * p.u_stride);
-      in[s] = {v.x, v.y};
+      for (int j = 0; j < VEC; j++) {
+        col[j] = cur.chunk * TILE + j * THREADS + threadIdx.x;
+        ok[j] = col[j] < g.n_inner;
+        fI[j] = axis_factors(p.tab_inner, p.N_inner, g.kb_inner + (ok[j] ? col[j] : 0));
+      }
     }
-    const int k0 = g.kb_outer + cur.a, k1 = g.kb_mid + cur.b, kI = g.kb_inner + col;
+    // every load of the tile first
+    double2 raw[VEC][NIN];
+#pragma unroll
+    for (int j = 0; j < VEC; j++)
+#pragma unroll
+      for (int s = 0; s < NIN; s++)
+        if (ok[j]) raw[j][s] = __ldcs(p.u + (cur.row * g.n_inner + col[j]) * p.u_mstride + s * p.u_stride);
+    const int k0 = g.kb_outer + cur.a, k1 = g.kb_mid + cur.b;
     const AxisFactors f0 = axis_factors(p.tab_outer, p.N_outer, k0);
     AxisFactors f1 = f0;
     if constexpr (DIM == 3) f1 = axis_factors(p.tab_mid, p.N_mid, k1);
-    Cplx out[NOUT];
-    const bool null_frequency = (k0 == 0) && (DIM == 2 || k1 == 0) && (kI == 0);   // bri17.hpp:327,334
-    if (null_frequency) {
 #pragma unroll
-      for (int s = 0; s < NOUT; s++) out[s] = {0., 0.};                            // :336-339
-    } else {
-      double phi[DIM], chi[DIM], psi[DIM], c[DIM], sh[DIM];
-      phi[0] = f0.phi; chi[0] = f0.chi; psi[0] = f0.psi; c[0] = f0.c; sh[0] = f0.s;
-      if constexpr (DIM == 3) { phi[1] = f1.phi; chi[1] = f1.chi; psi[1] = f1.psi; c[1] = f1.c; sh[1] = f1.s; }
-      phi[DIM - 1] = fI.phi; chi[DIM - 1] = fI.chi; psi[DIM - 1] = fI.psi; c[DIM - 1] = fI.c; sh[DIM - 1] = fI.s;
-      double K[DIM][DIM];
-      stiffness_entries<DIM>(phi, chi, psi, p.mu, p.scaling, K);
-      Cplx u[DIM];
-      if constexpr (MODE == 0) {
+    for (int j = 0; j < VEC; j++) {
+      if (!ok[j]) continue;
+      const long long i = cur.row * g.n_inner + col[j];
+      const int kI = g.kb_inner + col[j];
+      Cplx in[NIN];
 #pragma unroll
-        for (int d = 0; d < DIM; d++) u[d] = in[d];
-        cholesky_solve<DIM>(K, u);
+      for (int s = 0; s < NIN; s++) in[s] = {raw[j][s].x, raw[j][s].y};
+      Cplx out[NOUT];
+      const bool null_frequency = (k0 == 0) && (DIM == 2 || k1 == 0) && (kI == 0);   // bri17.hpp:327,334
+      if (null_frequency) {
 #pragma unroll
-        for (int d = 0; d < DIM; d++) out[d] = u[d];
+        for (int s = 0; s < NOUT; s++) out[s] = {0., 0.};                            // :336-339
       } else {
-        double sum_alpha = f0.alpha;
-        if constexpr (DIM == 3) sum_alpha = sum_alpha + f1.alpha;
-        sum_alpha = sum_alpha + fI.alpha;
-        double sn, cs;
-        sincos(sum_alpha, &sn, &cs);
-        Cplx B[DIM];
-        strain_displacement_entries<DIM>(c, sh, Cplx{-2. * sn, 2. * cs}, B);
-        eigenstress_to_displacement<DIM>(in, B, K, u);
-        if constexpr (MODE == 1) {
+        double phi[DIM], chi[DIM], psi[DIM], c[DIM], sh[DIM];
+        phi[0] = f0.phi; chi[0] = f0.chi; psi[0] = f0.psi; c[0] = f0.c; sh[0] = f0.s;
+        if constexpr (DIM == 3) { phi[1] = f1.phi; chi[1] = f1.chi; psi[1] = f1.psi; c[1] = f1.c; sh[1] = f1.s; }
+        phi[DIM - 1] = fI[j].phi; chi[DIM - 1] = fI[j].chi; psi[DIM - 1] = fI[j].psi;
+        c[DIM - 1] = fI[j].c; sh[DIM - 1] = fI[j].s;
+        double K[DIM][DIM];
+        stiffness_entries<DIM>(phi, chi, psi, p.mu, p.scaling, K);
+        Cplx u[DIM];
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int d = 0; d < DIM; d++) u[d] = in[d];
+          cholesky_solve<DIM>(K, u);
 #pragma unroll
           for (int d = 0; d < DIM; d++) out[d] = u[d];
         } else {
-          displacement_to_strain<DIM>(B, u, out);
+          double sum_alpha = f0.alpha;
+          if constexpr (DIM == 3) sum_alpha = sum_alpha + f1.alpha;
+          sum_alpha = sum_alpha + fI[j].alpha;
+          double sn, cs;
+          sincos(sum_alpha, &sn, &cs);
+          Cplx B[DIM];
+          strain_displacement_entries<DIM>(c, sh, Cplx{-2. * sn, 2. * cs}, B);
+          eigenstress_to_displacement<DIM>(in, B, K, u);
+          if constexpr (MODE == 1) {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) out[d] = u[d];
+          } else {
+            displacement_to_strain<DIM>(B, u, out);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int s = 0; s < NOUT; s++)
-      __stcs(p.f + i * p.f_mstride + s * p.f_stride, make_double2(out[s].re, out[s].im));
+      for (int s = 0; s < NOUT; s++)
+        __stcs(p.f + i * p.f_mstride + s * p.f_stride, make_double2(out[s].re, out[s].im));
+    }
   }
 }
 
@@ -937,15 +950,17 @@ int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, 
   ap.f = static_cast<double2 *>(out);
   ap.u_stride = in_cs; ap.u_mstride = in_ms;
   ap.f_stride = out_cs; ap.f_mstride = out_ms;
-  const int grid = make_geom(b, 256, p->sm_count * 2, &ap.g);
+  // two modes per thread for the lighter maps (more loads in flight), one for eigenstress -> strain
+  const int vec = (mode == 0 || (mode == 1 && b.dim == 2)) ? 2 : 1;   // register budget: no spills at 128
+  const int grid = make_geom(b, 256 * vec, p->sm_count * 2, &ap.g);
   if (b.dim == 3) {
-    if (mode == 0) modal_solve_kernel<3, 0><<<grid, 256, 0, stream>>>(ap);
-    else if (mode == 1) modal_solve_kernel<3, 1><<<grid, 256, 0, stream>>>(ap);
-    else modal_solve_kernel<3, 2><<<grid, 256, 0, stream>>>(ap);
+    if (mode == 0) modal_solve_kernel<3, 0, 2><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 1) modal_solve_kernel<3, 1, 1><<<grid, 256, 0, stream>>>(ap);
+    else modal_solve_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(ap);
   } else {
-    if (mode == 0) modal_solve_kernel<2, 0><<<grid, 256, 0, stream>>>(ap);
-    else if (mode == 1) modal_solve_kernel<2, 1><<<grid, 256, 0, stream>>>(ap);
-    else modal_solve_kernel<2, 2><<<grid, 256, 0, stream>>>(ap);
+    if (mode == 0) modal_solve_kernel<2, 0, 2><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 1) modal_solve_kernel<2, 1, 2><<<grid, 256, 0, stream>>>(ap);
+    else modal_solve_kernel<2, 2, 1><<<grid, 256, 0, stream>>>(ap);
   }
   p->launches++;
   return check_launch("modal_solve");

@@ -185,6 +185,9 @@ int bri17_plan_set_option(bri17_plan *p, const char *key, int64_t value) {
     if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "host_chunk_rows < 0");
     p->host_chunk_rows = value;
     free_host_stages(p);
+  } else if (!std::strcmp(key, "host_zero_copy")) {
+    p->host_zero_copy = value != 0;
+    free_host_stages(p);
   } else if (!std::strcmp(key, "host_streams")) {
     if (value < 1 || value > 8) return fail(BRI17_ERR_INVALID_ARG, "host_streams must be 1..8");
     p->host_streams = int(value);
