@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cg-iters", type=int, default=0, help="also time this many CG iterations")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="serialise the phases (gives the per-phase breakdown; default overlaps exchange and FFTs)")
     ap.add_argument("--real", action="store_true",
                     help="real float64 fields through the r2c half-spectrum path (default: complex, like the reference)")
     args = ap.parse_args()
@@ -58,6 +60,9 @@ def main():
     shape = (args.edge,) * 3
     L = tuple(n * h for n, h in zip(shape, SPACING))
     op = RealSpaceOperator.from_process_group(shape, L, MU, NU, device=local_rank, exchange_mode=args.mode)
+    if args.no_pipeline:
+        op.set_option("pipeline", 0)
+    pipelined = world > 1 and args.mode == 1 and not args.no_pipeline
     gen = torch.Generator(device=dev).manual_seed(4000 + rank)
     if args.real:
         u = torch.randn(op.real_shape, dtype=torch.float64, device=dev, generator=gen)
@@ -92,9 +97,12 @@ def main():
         "config": {"workload": f"3D Q8 {args.edge}^3 real-space apply, n0 slabs over {world} GPU(s)",
                    "fields": "real float64, r2c half spectrum" if args.real else "complex128 (c2c, as the reference)",
                    "exchange": ["nccl send/recv + pack/unpack kernels", "fused peer-store kernel (CUDA IPC over NVLink)"][args.mode]
-                   if world > 1 else "none (single GPU)"},
+                   if world > 1 else "none (single GPU)",
+                   "schedule": "exchange of component c overlapped with the FFTs of the other components (2 streams)"
+                   if pipelined else "phases serialised"},
         "phases_ms_last_apply_max_over_ranks": phases,
-        "exchange": None if world == 1 else {
+        "pipelined": pipelined,
+        "exchange": None if (world == 1 or pipelined) else {
             "bytes_sent_per_gpu_per_direction": xbytes,
             "fwd_gbs_per_gpu": xbytes / (phases["exchange_fwd"] * 1e-3) / 1e9,
             "bwd_gbs_per_gpu": xbytes / (phases["exchange_bwd"] * 1e-3) / 1e9,

@@ -50,6 +50,7 @@ RS_SIGNATURES = {
     "bri17_rs_plan_create": (C.c_int, [C.POINTER(_vp), C.c_int, _i32p, _f64p, C.c_double, C.c_double,
                                        C.c_int, C.c_int, C.c_int, _vp, C.c_int]),
     "bri17_rs_plan_destroy": (C.c_int, [_vp]),
+    "bri17_rs_plan_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "bri17_rs_plan_local": (C.c_int, [_vp, _i32p, _i32p, _i32p, _i32p]),
     "bri17_rs_plan_real_count": (C.c_int64, [_vp]),
     "bri17_rs_plan_fourier_count": (C.c_int64, [_vp]),

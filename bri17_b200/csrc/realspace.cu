@@ -83,12 +83,14 @@ struct CopyPlan {
 // list at its right-hand neighbour, so at any instant each GPU spreads its
 // stores over all peers and receives from all peers: an all-to-all that walks
 // the peers in lock step would serialise on one receiver's NVLink ingress.
+// The grid is capped (a few CTAs per SM walk the virtual CTA list) so that transform kernels
+// of the next/previous component can run beside it when the apply is pipelined.
 __global__ void __launch_bounds__(256) slab_copy_kernel(const CopyPlan cp, int fence_system) {
-  const long long cta = blockIdx.x;
+ for (long long cta = blockIdx.x; cta < cp.ctas_per_seg * cp.nseg; cta += gridDim.x) {
   const int s = int(cta % cp.nseg);
   const CopySeg &g = cp.seg[s];
   long long local = cta / cp.nseg;
-  if (local >= (long long)cp.ncomp * g.rows * cp.parts) return;
+  if (local >= (long long)cp.ncomp * g.rows * cp.parts) continue;
   const int part = int(local % cp.parts);
   local /= cp.parts;
   const int a = int(local % g.rows);
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(256) slab_copy_kernel(const CopyPlan cp, int f
     if (scaled) { v.x *= cp.scale; v.y *= cp.scale; }
     dst[i] = v;
   }
+ }
   if (fence_system) __threadfence_system();
 }
 
@@ -241,7 +244,11 @@ struct bri17_rs_plan {
   double correction = 1.0;     // |h|/|N|, tests/test_bri17.cpp:93-98
   Layout lc, lr;               // complex (c2c) and real (r2c) layouts
   bri17_plan *modal = nullptr;
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm = nullptr, comm_x = nullptr;   // comm_x: barriers on the exchange stream
+  cudaStream_t sx = nullptr;                      // exchange stream of the pipelined apply
+  cudaEvent_t ev_a[3] = {}, ev_b[3] = {};         // per-component hand-offs st <-> sx
+  int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
+  int copy_ctas = 148 * 4;                        // grid cap of slab_copy_kernel
   double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components of the c2c layout each
   size_t buf_bytes = 0;
   int64_t real_upper = 0;      // element offset of the upper region of W2 used by the real path
@@ -258,15 +265,15 @@ struct bri17_rs_plan {
 
 namespace {
 
-int launch_copy(CopyPlan &cp, int fence, cudaStream_t st) {
+int launch_copy(CopyPlan &cp, int fence, cudaStream_t st, int max_ctas) {
   long long per_seg = 0;
   for (int s = 0; s < cp.nseg; s++)
     per_seg = std::max(per_seg, (long long)cp.ncomp * cp.seg[s].rows * cp.parts);
   cp.ctas_per_seg = per_seg;
   const long long total = per_seg * cp.nseg;
   if (total == 0) return BRI17_OK;
-  if (total > 0x7fffffffLL) return fail(BRI17_ERR_UNSUPPORTED, "exchange grid too large");
-  slab_copy_kernel<<<(unsigned)total, 256, 0, st>>>(cp, fence);
+  const unsigned grid = unsigned(std::min<long long>(total, max_ctas));
+  slab_copy_kernel<<<grid, 256, 0, st>>>(cp, fence);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(BRI17_ERR_CUDA, std::string("slab_copy launch: ") + cudaGetErrorString(e));
   return BRI17_OK;
@@ -285,11 +292,18 @@ int stream_barrier(bri17_rs_plan *p, cudaStream_t st) {
   RS_NCCL_TRY(ncclAllReduce(p->barrier_word, p->barrier_word, 1, ncclDouble, ncclSum, p->comm, st));
   return BRI17_OK;
 }
+// same on the exchange stream of the pipelined apply, with its own communicator
+int exchange_barrier(bri17_rs_plan *p) {
+  RS_NCCL_TRY(ncclAllReduce(p->barrier_word + 8, p->barrier_word + 8, 1, ncclDouble, ncclSum, p->comm_x, p->sx));
+  return BRI17_OK;
+}
 
 // Forward exchange: local-transform layout T[c][a][b][k2] (a in my n0 slab, b over S1)
 // -> Fourier-side layout X[c][n0][b_loc][k2].  `S` is the packed send buffer (mode 0).
+// c0/ncomp select components of the multi-component arrays T and X; `barriers` = false leaves
+// the cross-GPU synchronisation to the caller (pipelined apply).
 int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double2 *X, double2 *S, int ncomp,
-                     cudaStream_t st) {
+                     cudaStream_t st, int c0 = 0, bool barriers = true) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   CopyPlan cp{};
   cp.ncomp = ncomp;
@@ -303,18 +317,18 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
     const int n1q = l.k1_beg[q + 1] - l.k1_beg[q];
     if (n1q == 0 || p->n0_loc == 0) continue;
     CopySeg &g = cp.seg[cp.nseg++];
-    g.src = T + (long long)l.k1_beg[q] * S2e;
     g.src_cs = (long long)p->n0_loc * S1 * S2e;
     g.src_rs = (long long)S1 * S2e;
+    g.src = T + (long long)l.k1_beg[q] * S2e + c0 * g.src_cs;
     g.rows = p->n0_loc;
     g.len = n1q * S2e;
     maxlen = std::max(maxlen, g.len);
     const bool direct = (q == r) || p->mode == 1;  // store at the final position
     if (direct) {
       double2 *base = (q == r) ? X : p->peerW[q];
-      g.dst = base + (long long)p->n0_beg[r] * n1q * S2e;
       g.dst_cs = (long long)N0 * n1q * S2e;
       g.dst_rs = (long long)n1q * S2e;
+      g.dst = base + (long long)p->n0_beg[r] * n1q * S2e + c0 * g.dst_cs;
     } else {
       g.dst = S + off[q];
       g.dst_cs = (long long)p->n0_loc * n1q * S2e;
@@ -322,10 +336,10 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
     }
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * p->n0_loc * P);
-  if (p->mode == 1) RS_TRY(stream_barrier(p, st));  // peers' buffers are free to overwrite
-  RS_TRY(launch_copy(cp, p->mode == 1, st));
+  if (p->mode == 1 && barriers) RS_TRY(stream_barrier(p, st));  // peers' buffers are free to overwrite
+  RS_TRY(launch_copy(cp, p->mode == 1, st, p->copy_ctas));
   if (P == 1) return BRI17_OK;
-  if (p->mode == 1) return stream_barrier(p, st);   // everybody's stores have landed
+  if (p->mode == 1) return barriers ? stream_barrier(p, st) : BRI17_OK;   // everybody's stores have landed
   RS_NCCL_TRY(ncclGroupStart());
   for (int q = 0; q < P; q++) {
     if (q == r) continue;
@@ -345,7 +359,7 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
 // Backward exchange: Fourier-side X[c][n0][b_loc][k2] -> local-transform layout D[c][a][b][k2] (times scale).
 // mode 0: R = packed receive buffer, D written by the unpack; mode 1: peers store into our W2 (= D).
 int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, double2 *D, double2 *R, int ncomp,
-                      double scale, cudaStream_t st) {
+                      double scale, cudaStream_t st, int c0 = 0, bool barriers = true) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   if (p->mode == 1 || P == 1) {
     // every row (c, n0) goes, whole, to the owner of n0, at its final position
@@ -357,20 +371,20 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
       const int n0q = p->n0_beg[q + 1] - p->n0_beg[q];
       if (n0q == 0 || l.n1_loc == 0) continue;
       CopySeg &g = cp.seg[cp.nseg++];
-      g.src = X + (long long)p->n0_beg[q] * l.n1_loc * S2e;
       g.src_cs = (long long)N0 * l.n1_loc * S2e;
       g.src_rs = (long long)l.n1_loc * S2e;
+      g.src = X + (long long)p->n0_beg[q] * l.n1_loc * S2e + c0 * g.src_cs;
       g.rows = n0q;
       g.len = l.n1_loc * S2e;
       double2 *base = (q == r) ? D : p->peerW2[q];
-      g.dst = base + (long long)l.k1_beg[r] * S2e;
       g.dst_cs = (long long)n0q * S1 * S2e;
       g.dst_rs = (long long)S1 * S2e;
+      g.dst = base + (long long)l.k1_beg[r] * S2e + c0 * g.dst_cs;
     }
     cp.parts = choose_parts(l.n1_loc * S2e, (long long)ncomp * N0);
-    RS_TRY(stream_barrier(p, st));
-    RS_TRY(launch_copy(cp, P > 1, st));
-    return stream_barrier(p, st);
+    if (barriers) RS_TRY(stream_barrier(p, st));
+    RS_TRY(launch_copy(cp, P > 1, st, p->copy_ctas));
+    return barriers ? stream_barrier(p, st) : BRI17_OK;
   }
   std::vector<long long> off(P + 1, 0);
   for (int q = 0; q < P; q++)
@@ -413,7 +427,7 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
     g.dst_rs = (long long)S1 * S2e;
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * p->n0_loc * P);
-  return launch_copy(cp, 0, st);
+  return launch_copy(cp, 0, st, p->copy_ctas);
 }
 
 // c2c local transform over the trailing axes (complex layout only)
@@ -595,6 +609,57 @@ int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long
   return BRI17_OK;
 }
 
+// Pipelined apply for nranks > 1 with the fused peer-store exchange: the exchange of
+// component c runs on its own high-priority stream while the transforms of the other
+// components run on the caller's stream, so NVLink-bound and HBM-bound work overlap.
+//   st: L0 L1 L2 |wait| A0 A1 A2  modal  A'0 A'1 A'2 |wait| L'0 L'1 L'2
+//   sx:    P0 P1 P2 (push + barrier each)        Q0 Q1 Q2 (push back + barrier each)
+// L = local transform over the trailing axes, A = axis-0 transform, P/Q = slab_copy_kernel
+// storing into the peers' W / W2.  No "buffer free" barrier is needed: every exchange ends
+// with a barrier after its last read, and the next writer is ordered behind it.
+template <typename LocalFwd, typename LocalInv>
+int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFwd local_fwd, LocalInv local_inv,
+                    cudaStream_t st) {
+  const int dim = p->dim;
+  double2 *X = p->W;
+  p->timings_valid = false;
+  mark(p, 0, st);
+  for (int c = 0; c < dim; c++) {
+    RS_TRY(local_fwd(c));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
+    RS_TRY(exchange_forward(p, l, T, X, nullptr, 1, p->sx, c, false));
+    RS_TRY(exchange_barrier(p));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
+  }
+  mark(p, 1, st);
+  mark(p, 2, st);
+  for (int c = 0; c < dim; c++) {
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
+    RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_FORWARD, st));
+  }
+  mark(p, 3, st);
+  RS_TRY(modal_on_block(p, l, X, st));
+  mark(p, 4, st);
+  for (int c = 0; c < dim; c++) {
+    RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_INVERSE, st));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
+    RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
+    RS_TRY(exchange_barrier(p));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
+  }
+  mark(p, 5, st);
+  mark(p, 6, st);
+  for (int c = 0; c < dim; c++) {
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
+    RS_TRY(local_inv(c));
+  }
+  mark(p, 7, st);
+  p->timings_valid = true;
+  return BRI17_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -617,7 +682,11 @@ int bri17_rs_plan_destroy(bri17_rs_plan *p) {
     if (p->peerW[q]) cudaIpcCloseMemHandle(p->peerW[q]);
     if (p->peerW2[q]) cudaIpcCloseMemHandle(p->peerW2[q]);
   }
+  if (p->comm_x) ncclCommDestroy(p->comm_x);
   if (p->comm) ncclCommDestroy(p->comm);
+  if (p->sx) cudaStreamDestroy(p->sx);
+  for (auto &e : p->ev_a) if (e) cudaEventDestroy(e);
+  for (auto &e : p->ev_b) if (e) cudaEventDestroy(e);
   destroy_layout(p->lc);
   destroy_layout(p->lr);
   for (void *ptr : {(void *)p->W, (void *)p->W2, (void *)p->barrier_word, (void *)p->cg_r, (void *)p->cg_p,
@@ -690,6 +759,18 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
       return bail(fail(BRI17_ERR_CUDA, "exchange buffer allocation failed"));
     p->buf_bytes = cap;
     cudaMemset(p->barrier_word, 0, 256);
+    {  // exchange stream (high priority), its events and its own communicator
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&p->sx, cudaStreamNonBlocking, hi) != cudaSuccess)
+        return bail(fail(BRI17_ERR_CUDA, "exchange stream creation failed"));
+      for (int c = 0; c < 3; c++)
+        if (cudaEventCreateWithFlags(&p->ev_a[c], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p->ev_b[c], cudaEventDisableTiming) != cudaSuccess)
+          return bail(fail(BRI17_ERR_CUDA, "cudaEventCreate failed"));
+      nr = ncclCommSplit(p->comm, 0, rank, &p->comm_x, nullptr);
+      if (nr != ncclSuccess) return bail(fail(BRI17_ERR_NCCL, std::string("ncclCommSplit: ") + ncclGetErrorString(nr)));
+    }
     if (p->mode == 1) {
       // exchange CUDA-IPC handles of W and W2 through NCCL itself
       struct Handles { cudaIpcMemHandle_t w, w2; };
@@ -806,6 +887,11 @@ int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev,
   const double2 *u = static_cast<const double2 *>(u_dev);
   double2 *F = static_cast<double2 *>(F_dev);
   const int dim = p->dim;
+  if (p->nranks > 1 && p->mode == 1 && p->pipeline) {
+    auto fwd = [&](int c) { return fft_local_c2c(p, u + c * l.t_count, F + c * l.t_count, 1, CUFFT_FORWARD, st); };
+    auto inv = [&](int c) { return fft_local_c2c(p, p->W2 + c * l.t_count, F + c * l.t_count, 1, CUFFT_INVERSE, st); };
+    return apply_pipelined(p, l, F, fwd, inv, st);
+  }
   p->timings_valid = false;
   mark(p, 0, st);
   RS_TRY(fft_local_c2c(p, u, F, dim, CUFFT_FORWARD, st));                   // :57 (axes 1..)
@@ -855,23 +941,36 @@ int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F
   const double *u = static_cast<const double *>(u_dev);
   double *F = static_cast<double *>(F_dev);
   double2 *T = p->W2;  // local-transform layout [c][n0_loc][S1][S2e]
-  p->timings_valid = false;
-  mark(p, 0, st);
   // cuFFT wants 16-byte aligned real arrays; component c starts at c*real_count doubles, which
   // is misaligned when the slab holds an odd number of values: stage those through rbuf.
   if ((p->real_count & 1) && !p->rbuf) BRI17_CUDA_TRY(cudaMalloc(&p->rbuf, sizeof(double) * (p->real_count + 2)));
   auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; };
-  if (l.have_local) {
+  auto local_fwd = [&](int c) -> int {  // D2Z u_c -> T_c
+    if (!l.have_local) return BRI17_OK;
     RS_CUFFT_TRY(cufftSetStream(l.fwd_local, st));
-    for (int c = 0; c < dim; c++) {
-      double *src = const_cast<double *>(u) + c * p->real_count;
-      if (misaligned(src)) {
-        BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
-        src = p->rbuf;
-      }
-      RS_CUFFT_TRY(cufftExecD2Z(l.fwd_local, src, (cufftDoubleComplex *)(T + c * l.t_count)));
+    double *src = const_cast<double *>(u) + c * p->real_count;
+    if (misaligned(src)) {
+      BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
+      src = p->rbuf;
     }
-  }
+    RS_CUFFT_TRY(cufftExecD2Z(l.fwd_local, src, (cufftDoubleComplex *)(T + c * l.t_count)));
+    return BRI17_OK;
+  };
+  auto local_inv = [&](int c) -> int {  // Z2D (W2)_c -> F_c
+    if (!l.have_local) return BRI17_OK;
+    RS_CUFFT_TRY(cufftSetStream(l.inv_local, st));
+    double *dst = F + c * p->real_count;
+    double *out = misaligned(dst) ? p->rbuf : dst;
+    RS_CUFFT_TRY(cufftExecZ2D(l.inv_local, (cufftDoubleComplex *)(p->W2 + c * l.t_count), out));
+    if (out != dst)
+      BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
+    return BRI17_OK;
+  };
+  if (p->nranks > 1 && p->mode == 1 && p->pipeline) return apply_pipelined(p, l, T, local_fwd, local_inv, st);
+
+  p->timings_valid = false;
+  mark(p, 0, st);
+  for (int c = 0; c < dim; c++) RS_TRY(local_fwd(c));
   mark(p, 1, st);
   double2 *X = T;
   if (p->nranks > 1) {
@@ -886,7 +985,6 @@ int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F
   mark(p, 4, st);
   RS_TRY(fft_axis0(p, l, X, dim, CUFFT_INVERSE, st));
   mark(p, 5, st);
-  double2 *D = T;
   if (p->nranks > 1) {
     if (p->mode == 1) {
       RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));   // peers store into our W2
@@ -894,21 +992,21 @@ int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F
       double2 *R = p->W2 + p->real_upper;                                 // packed receive pieces
       RS_TRY(exchange_backward(p, l, X, p->W2, R, dim, 1.0, st));
     }
-    D = p->W2;
   }
   mark(p, 6, st);
-  if (l.have_local) {
-    RS_CUFFT_TRY(cufftSetStream(l.inv_local, st));
-    for (int c = 0; c < dim; c++) {
-      double *dst = F + c * p->real_count;
-      double *out = misaligned(dst) ? p->rbuf : dst;
-      RS_CUFFT_TRY(cufftExecZ2D(l.inv_local, (cufftDoubleComplex *)(D + c * l.t_count), out));
-      if (out != dst)
-        BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
-    }
-  }
+  for (int c = 0; c < dim; c++) RS_TRY(local_inv(c));
   mark(p, 7, st);
   p->timings_valid = true;
+  return BRI17_OK;
+}
+
+int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
+  if (!p || !key) return fail(BRI17_ERR_INVALID_ARG, "plan/key is NULL");
+  if (!std::strcmp(key, "pipeline")) p->pipeline = value != 0;
+  else if (!std::strcmp(key, "copy_ctas")) {
+    if (value < 1) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 1");
+    p->copy_ctas = int(value);
+  } else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown option ") + key);
   return BRI17_OK;
 }
 

@@ -67,6 +67,9 @@ class RealSpaceOperator:
         return cls(shape, L, mu, nu, device=device, rank=rank, world=world, unique_id=box[0],
                    exchange_mode=exchange_mode)
 
+    def set_option(self, key, value):
+        check(self._lib.bri17_rs_plan_set_option(self._plan, key.encode(), int(value)))
+
     def close(self):
         plan, self._plan = getattr(self, "_plan", None), None
         if plan:

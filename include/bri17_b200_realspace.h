@@ -58,6 +58,11 @@ BRI17_API int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shap
                                    const void *nccl_unique_id, int exchange_mode);
 BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
 
+/* Tuning knobs: "pipeline" (1 = overlap the exchange of one component with the
+ * transforms of the others on a second stream; default 1, fused exchange only),
+ * "copy_ctas" (grid cap of the exchange kernel). */
+BRI17_API int bri17_rs_plan_set_option(bri17_rs_plan *plan, const char *key, int64_t value);
+
 /* Geometry of this rank: real-space slab [n0_begin, n0_begin+n0_count) of axis
  * 0, Fourier-space slab [k1_begin, k1_begin+k1_count) of axis 1. */
 BRI17_API int bri17_rs_plan_local(const bri17_rs_plan *plan, int *n0_begin, int *n0_count,

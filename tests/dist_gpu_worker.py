@@ -26,7 +26,7 @@ def main():
     o = oracle.best()
     ok = True
     worst = 0.0
-    for mode in (0, 1):
+    for mode, pipeline in ((0, 0), (1, 0), (1, 1)):
         for shape in ((9, 7, 5), (16, 12, 10), (12, 10), (32, 32, 32)):
             dim = len(shape)
             L = tuple(n * h for n, h in zip(shape, (1.1, 1.2, 1.3)))
@@ -35,6 +35,7 @@ def main():
             u -= u.mean(axis=tuple(range(1, dim + 1)), keepdims=True)
             ref = real_space_apply_ref(o, shape, L, MU, NU, u + 0j)
             op = RealSpaceOperator.from_process_group(shape, L, MU, NU, device=local, exchange_mode=mode)
+            op.set_option("pipeline", pipeline)
             a0, a1 = op.n0_begin, op.n0_begin + op.n0_count
             ud = torch.from_numpy(np.ascontiguousarray(u[:, a0:a1]) + 0j).cuda()
             for _ in range(2):                       # twice: buffer reuse across applies
@@ -67,7 +68,7 @@ def main():
             good = err <= 1e-13 and cg_err <= 1e-7 and res <= 1e-11
             ok &= good
             if rank == 0:
-                print(f"mode {mode} shape {shape}: apply/fft err {err:.2e}, cg iters {iters} res {res:.1e} "
+                print(f"mode {mode} pipeline {pipeline} shape {shape}: apply/fft err {err:.2e}, cg iters {iters} res {res:.1e} "
                       f"err {cg_err:.1e} {'ok' if good else 'FAIL'}", flush=True)
             op.close()
     if rank == 0:
