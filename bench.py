@@ -149,7 +149,8 @@ def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    workload = f"3D Q8 {args.edge}^3 modal stiffness apply (BASELINE configs[2])"
+    workload = (f"3D Q8 {args.edge}^3 modal stiffness apply per GPU (BASELINE configs[2]); "
+                "reference CPU path (tests/test_bri17.cpp:76-91 loop over Hooke::modal_stiffness), host cores only")
     value, dt, descr = cpu_reference_leg(args.edge, max(1, args.steps), max(0, args.warmup),
                                          target_step_s=0.25)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,

@@ -69,12 +69,33 @@ _lib = None
 _rs_lib = None
 
 
+def _preload_wheel_libs() -> None:
+    """libbri17_b200_rs.so needs libnccl.so.2 and libcufft.so.11.  When the PyTorch wheels are
+    installed, load THEIR copies first (what `import torch` would do): the dynamic loader keeps
+    one library per soname, and torch does not import against the older system NCCL."""
+    import importlib.util
+    for pkg, name in (("nvidia.nccl", "libnccl.so.2"), ("nvidia.cufft", "libcufft.so.11")):
+        try:
+            spec = importlib.util.find_spec(pkg)
+        except (ImportError, ValueError):
+            spec = None
+        for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+            path = os.path.join(base, "lib", name)
+            if os.path.exists(path):
+                try:
+                    C.CDLL(path, mode=C.RTLD_GLOBAL)
+                except OSError:
+                    pass
+                break
+
+
 def load_rs() -> C.CDLL:
     """Load libbri17_b200_rs.so (cuFFT + NCCL layer); no fallback."""
     global _rs_lib
     if _rs_lib is not None:
         return _rs_lib
     load()
+    _preload_wheel_libs()
     if not os.path.exists(RS_LIB_PATH):
         raise RuntimeError(f"{RS_LIB_PATH} is missing: build it with `python -m bri17_b200.build`")
     lib = C.CDLL(RS_LIB_PATH)

@@ -40,6 +40,9 @@
 
 #ifndef BRI17_NO_DEVICE
 #include "bri17_b200.h"
+#ifdef BRI17_WITH_REALSPACE
+#include "bri17_b200_realspace.h"
+#endif
 #endif
 
 namespace bri17 {
@@ -379,6 +382,68 @@ class ModalOperator {
   Hooke<double, DIM> hooke_;
   bri17_plan *plan_ = nullptr;
 };
+#ifdef BRI17_WITH_REALSPACE
+// ---------------------------------------------------------------------------
+// RealSpaceOperator: F = (|h|/|N|) iDFT(K^ DFT(u)), i.e. the whole
+// StiffnessMatrixFactory::compute_Ku of the reference harness
+// (tests/test_bri17.cpp:56-107) on the GPU (cuFFT instead of FFTW), optionally
+// slab-distributed over `nranks` processes, plus matrix-free CG.  Define
+// BRI17_WITH_REALSPACE and link libbri17_b200_rs.so.
+// Fields: [DIM][n0_count][N1][(N2)] of this rank's slab, complex<double>
+// (real data carried as complex, like the reference) or plain double (r2c path).
+// ---------------------------------------------------------------------------
+template <int DIM>
+  requires(DIM == 2 || DIM == 3)
+class RealSpaceOperator {
+ public:
+  using complex_t = std::complex<double>;
+
+  explicit RealSpaceOperator(const Hooke<double, DIM> &hooke, int device = 0, int rank = 0, int nranks = 1,
+                             const void *nccl_unique_id = nullptr, int exchange_mode = 1) {
+    check(bri17_rs_plan_create(&plan_, DIM, hooke.grid.shape.data(), hooke.grid.L.data(), hooke.mu, hooke.nu,
+                               device, rank, nranks, nccl_unique_id, exchange_mode));
+    bri17_rs_plan_local(plan_, &n0_begin_, &n0_count_, nullptr, nullptr);
+  }
+  ~RealSpaceOperator() { bri17_rs_plan_destroy(plan_); }
+  RealSpaceOperator(const RealSpaceOperator &) = delete;
+  RealSpaceOperator &operator=(const RealSpaceOperator &) = delete;
+
+  int n0_begin() const { return n0_begin_; }
+  int n0_count() const { return n0_count_; }
+  std::int64_t slab_count() const { return bri17_rs_plan_real_count(plan_); }  // elements per component
+
+  void apply(const complex_t *u_dev, complex_t *F_dev, void *stream = nullptr) const {
+    check(bri17_real_space_apply_f64(plan_, u_dev, F_dev, stream));
+  }
+  void apply(const double *u_dev, double *F_dev, void *stream = nullptr) const {
+    check(bri17_real_space_apply_real_f64(plan_, u_dev, F_dev, stream));
+  }
+  // Conjugate gradients on A x = b (zero-mean b); returns the iteration count.
+  int solve(const complex_t *b_dev, complex_t *x_dev, double rtol = 1e-8, int max_iter = 1000,
+            double *rel_residual = nullptr, void *stream = nullptr) const {
+    int it = 0;
+    check(bri17_cg_solve_f64(plan_, b_dev, x_dev, rtol, max_iter, 10, &it, rel_residual, stream));
+    return it;
+  }
+  int solve(const double *b_dev, double *x_dev, double rtol = 1e-8, int max_iter = 1000,
+            double *rel_residual = nullptr, void *stream = nullptr) const {
+    int it = 0;
+    check(bri17_cg_solve_real_f64(plan_, b_dev, x_dev, rtol, max_iter, 10, &it, rel_residual, stream));
+    return it;
+  }
+  bri17_rs_plan *c_plan() const { return plan_; }
+
+ private:
+  static void check(int rc) {
+    if (rc == BRI17_OK) return;
+    const std::string msg = bri17_last_error();
+    if (rc == BRI17_ERR_INVALID_ARG) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+  }
+  bri17_rs_plan *plan_ = nullptr;
+  int n0_begin_ = 0, n0_count_ = 0;
+};
+#endif  // BRI17_WITH_REALSPACE
 #endif  // BRI17_NO_DEVICE
 
 }  // namespace bri17

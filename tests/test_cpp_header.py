@@ -117,3 +117,17 @@ def test_modal_operator_cpp_program():
     print(out.stdout, out.stderr)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("max_abs_diff 0.000e+00 invalid_argument_thrown 1") == 2
+
+
+@pytest.mark.gpu
+def test_real_space_cpp_program():
+    """tests/cpp/test_real_space.cpp: the reference's global-assembly check written in
+    C++ against bri17::RealSpaceOperator (c2c and r2c paths, CG)."""
+    exe = os.path.join(CPP, "test_real_space")
+    if not os.path.exists(exe):
+        out = subprocess.run(["make", "-C", CPP, "test_real_space"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(out.stdout, out.stderr)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" OK") == 2
