@@ -35,6 +35,8 @@ SIGNATURES = {
     "bri17_modal_strain_displacement_field_f64": (C.c_int, [_vp, _vp, _i32p, _i32p, _vp]),
     "bri17_strain_displacement_apply_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_int64, C.c_double, _vp]),
     "bri17_freq_index_map": (C.c_int, [_vp, _vp, _i32p, _i32p, _vp]),
+    "bri17_debug_walk_tiles": (C.c_int, [_vp, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64),
+                                         C.c_int, _i32p]),
     "bri17_modal_eigenstress_to_opposite_strain_mode_f64": (C.c_int, [_vp, _i32p, _f64p, _f64p]),
     "bri17_modal_stiffness_solve_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_int64, _vp]),
     "bri17_eigenstress_to_displacement_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_int64,

@@ -132,6 +132,7 @@ int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
 // mode: 0 u^ = K^-1 f^; 1 u^ = K^-1 (tau^ . conj B^); 2 eta^ = sym(B^ (x) u^) of mode 1
 int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, void *out,
                        int64_t in_cs, int64_t in_ms, int64_t out_cs, int64_t out_ms, cudaStream_t stream);
+int walk_tiles_host(const Block &b, int tile_modes, int max_ctas, int cta, int64_t *out, int cap, int *grid_out);
 int apply_host(bri17_plan *p, const Block &b, const void *u_host, void *f_host,
                int64_t comp_stride, double out_scale);
 void free_host_stages(bri17_plan *p);

@@ -80,16 +80,16 @@ struct TileCursor {
   int chunk;      // which TILE-wide piece of the row
   int a, b;       // row = a * n_mid + b
 
-  __device__ __forceinline__ void init(const TileGeom &g) {
-    tile = blockIdx.x;
+  __host__ __device__ __forceinline__ void init(const TileGeom &g, unsigned block) {
+    tile = block;
     row = tile / g.cpr;
     chunk = int(tile - row * g.cpr);
     a = int(row / g.n_mid);
     b = int(row - (long long)a * g.n_mid);
   }
-  __device__ __forceinline__ bool valid(const TileGeom &g) const { return tile < g.n_tiles; }
-  __device__ __forceinline__ void next(const TileGeom &g) {
-    tile += gridDim.x;
+  __host__ __device__ __forceinline__ bool valid(const TileGeom &g) const { return tile < g.n_tiles; }
+  __host__ __device__ __forceinline__ void next(const TileGeom &g, unsigned grid) {
+    tile += grid;
     row += g.d_row;
     chunk += g.d_chunk;
     a += g.d_a;
@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_kernel(co
   const bool scale_out = p.out_scale != 1.0;
 
   TileCursor cur;
-  cur.init(g);
+  cur.init(g, blockIdx.x);
   int cached_chunk = -1;
   int col[VEC];
   bool ok[VEC];
   double phiI[VEC], chiI[VEC], psiI[VEC];  // fastest-axis table entries of my columns
 
-  for (; cur.valid(g); cur.next(g)) {
+  for (; cur.valid(g); cur.next(g, gridDim.x)) {
     if (cur.chunk != cached_chunk) {  // CTA-uniform; taken once when gridDim.x % cpr == 0
       cached_chunk = cur.chunk;
 #pragma unroll
@@ -418,7 +418,7 @@ template <int DIM>
 __global__ void __launch_bounds__(256) freq_index_map_kernel(const TileGeom g, int32_t *k_out) {
   constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
   TileCursor cur;
-  for (cur.init(g); cur.valid(g); cur.next(g)) {
+  for (cur.init(g, blockIdx.x); cur.valid(g); cur.next(g, gridDim.x)) {
     const long long base = cur.row * g.n_inner;
 #pragma unroll
     for (int j = 0; j < VEC; j++) {
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) modal_stiffness_field_kernel(const ApplyP
   const double mu = p.mu, scaling = p.scaling;
   double2 *K = p.f;
   TileCursor cur;
-  for (cur.init(g); cur.valid(g); cur.next(g)) {
+  for (cur.init(g, blockIdx.x); cur.valid(g); cur.next(g, gridDim.x)) {
     const long long base = cur.row * g.n_inner;
     const int ka = g.kb_outer + cur.a;
     const double p0 = __ldg(p.tab_outer + ka), c0 = __ldg(p.tab_outer + p.N_outer + ka),
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(256, 2) strain_displacement_kernel(const Apply
   int col[VEC];
   bool ok[VEC];
   HalfAngle hI[VEC];
-  for (cur.init(g); cur.valid(g); cur.next(g)) {
+  for (cur.init(g, blockIdx.x); cur.valid(g); cur.next(g, gridDim.x)) {
     if (cur.chunk != cached_chunk) {
       cached_chunk = cur.chunk;
 #pragma unroll
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256, 2) modal_solve_kernel(const ApplyParams p
   int col[VEC];
   bool ok[VEC];
   AxisFactors fI[VEC];
-  for (cur.init(g); cur.valid(g); cur.next(g)) {
+  for (cur.init(g, blockIdx.x); cur.valid(g); cur.next(g, gridDim.x)) {
     if (cur.chunk != cached_chunk) {
       cached_chunk = cur.chunk;
 #pragma unroll
@@ -964,6 +964,26 @@ int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, 
   }
   p->launches++;
   return check_launch("modal_solve");
+}
+
+// Host replay of the tile cursor of one persistent CTA (diagnostic, no device needed):
+// writes (tile, row, chunk, a, b) per visited tile.  Lets the CPU tests check that the
+// division-free stepping covers every tile exactly once with consistent indices.
+int walk_tiles_host(const Block &b, int tile_modes, int max_ctas, int cta, int64_t *out, int cap, int *grid_out) {
+  TileGeom g;
+  const int grid = make_geom(b, tile_modes, max_ctas, &g);
+  if (grid_out) *grid_out = grid;
+  if (cta < 0 || cta >= grid) return 0;
+  TileCursor cur;
+  int n = 0;
+  for (cur.init(g, unsigned(cta)); cur.valid(g); cur.next(g, unsigned(grid))) {
+    if (n < cap) {
+      out[5 * n + 0] = cur.tile; out[5 * n + 1] = cur.row; out[5 * n + 2] = cur.chunk;
+      out[5 * n + 3] = cur.a; out[5 * n + 4] = cur.b;
+    }
+    n++;
+  }
+  return n;
 }
 
 }  // namespace bri17b200

@@ -447,6 +447,15 @@ int bri17_strain_displacement_apply_f64(bri17_plan *p, const void *u, void *eps,
   });
 }
 
+int bri17_debug_walk_tiles(const bri17_plan *p, const int *k_begin, const int *local_shape, int tile_modes,
+                           int max_ctas, int cta, int64_t *out, int cap, int *grid) {
+  if (!p || !out || tile_modes < 1 || max_ctas < 1) return -1;
+  Block b;
+  if (make_block(p, k_begin, local_shape, &b)) return -1;
+  if (b.modes == 0) return 0;
+  return walk_tiles_host(b, tile_modes, max_ctas, cta, out, cap, grid);
+}
+
 int bri17_freq_index_map(bri17_plan *p, int32_t *k_out, const int *k_begin,
                          const int *local_shape, void *stream) {
   if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");

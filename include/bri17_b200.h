@@ -192,6 +192,15 @@ BRI17_API int bri17_eigenstress_to_opposite_strain_f64(bri17_plan *plan, const v
 BRI17_API int bri17_freq_index_map(bri17_plan *plan, int32_t *k_out_dev, const int *k_begin,
                          const int *local_shape, void *stream);
 
+/* Diagnostic, host only (works on a BRI17_DEVICE_NONE plan): replays on the CPU the
+ * tile cursor that persistent CTA `cta` of a grid of at most `max_ctas` CTAs follows over
+ * the block, for tiles of `tile_modes` modes.  Writes (tile, row, chunk, a, b) per visited
+ * tile into out[5*i..] (up to `cap` tiles), the grid size into *grid, and returns the
+ * number of tiles visited (-1 on bad arguments). */
+BRI17_API int bri17_debug_walk_tiles(const bri17_plan *plan, const int *k_begin, const int *local_shape,
+                                     int tile_modes, int max_ctas, int cta, int64_t *out, int cap,
+                                     int *grid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -306,6 +306,11 @@ def test_large_3d_512_sampled_slabs(oracle_mod):
     lhs = torch.sum(torch.conj(v) * fs)
     rhs = torch.sum(torch.conj(Kv) * us)
     assert abs(complex(lhs - rhs)) <= 1e-11 * abs(complex(lhs))
+    # index map on 512^3 slabs: a k0 slab (modal apply at N>1) and a k1 slab (the Fourier-side
+    # block of the distributed real-space apply), bit-exact against the row-major loop nest
+    for kb, loc in (((504, 0, 0), (8, 512, 512)), ((0, 448, 0), (16, 64, 512)), ((100, 200, 0), (3, 5, 257))):
+        k = op.freq_index_map(loc, kb).cpu().numpy()
+        assert np.array_equal(k, oracle_mod.freq_index_map(kb, loc))
     # slabs reproduce the full-grid result bit for bit (what each GPU computes at N>1)
     fs2 = op.apply_modal_stiffness(u[:, 448:512].contiguous(), k_begin=(448, 0, 0))
     assert torch.equal(torch.view_as_real(fs2), torch.view_as_real(f[:, 448:512]))
