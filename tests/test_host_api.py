@@ -185,3 +185,17 @@ def test_product_does_not_import_oracle():
                     src = open(os.path.join(dirpath, fn), errors="ignore").read()
                     hit = re.search(r"(from|import)\s+oracle|liboracle|oracle/|_ref/|libbri17_ref", src)
                     assert hit is None, (os.path.join(dirpath, fn), hit.group(0))
+
+
+def test_pybri17_module_name():
+    """`import pybri17` exposes the reference's Python names (python/pybri17.cpp:98-107)."""
+    import pybri17
+    for name in ("CartesianGrid2f64", "CartesianGrid3f64", "Hooke2f64", "Hooke3f64"):
+        assert hasattr(pybri17, name)
+    grid = pybri17.CartesianGrid2f64((4, 4), (1.0, 1.0))
+    hooke = pybri17.Hooke2f64(1.0, 0.3, grid)
+    assert (hooke.mu, hooke.nu, hooke.grid) == (1.0, 0.3, grid) and grid.dim == 2
+    for method in ("modal_strain_displacement", "modal_stiffness_matrix",
+                   "modal_eigenstress_to_opposite_strain"):
+        assert callable(getattr(hooke, method))
+    assert pybri17.__version__ == "0.1"
