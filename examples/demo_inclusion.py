@@ -33,7 +33,7 @@ print(grid, hooke, sep="\n", end="")
 patch = N // 8
 tau = torch.zeros(shape + (sym,), dtype=torch.complex128, device="cuda")
 tau[:patch, :patch, -1] = 1.0
-tau_hat = torch.fft.fftn(tau, dim=(0, 1))
+tau_hat = torch.fft.fftn(tau, dim=(0, 1)).contiguous()     # mode-major (k0, k1, sym), C order
 
 op = pybri17.ModalOperator(shape, L, mu, nu)
 torch.cuda.synchronize()
