@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The shared libraries are build artefacts (git-ignored).  The product loader refuses to run
+    # without them; the test session builds them once if a fresh checkout has none.
+    from bri17_b200 import _lib
+    if not (os.path.exists(_lib.LIB_PATH) and os.path.exists(_lib.RS_LIB_PATH)):
+        from bri17_b200 import build
+        build.build()
 
 
 @pytest.fixture(scope="session")
