@@ -96,7 +96,6 @@ struct bri17_plan {
   double scaling = 0;  // mu / (1 - 2 nu), bri17.hpp:266
   int device = 0;
   int sm_count = 0;
-  int max_smem_optin = 0;
   bri17b200::AxisTables tab[3];
   int apply_variant = -1;  // -1: default
   int mapping = 0;         // 0 auto, 1 always row tiles, 2 always flat tiles

@@ -139,8 +139,6 @@ int bri17_plan_create(bri17_plan **out, int dim, const int *shape, const double 
 
   int rc = BRI17_OK;
   cudaError_t ce = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (ce == cudaSuccess)
-    ce = cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   for (int d = 0; d < dim && ce == cudaSuccess; d++) {
     fill_axis_tables(p->tab[d], shape[d], L[d]);
     const size_t bytes = p->tab[d].host.size() * sizeof(double);
