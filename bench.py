@@ -109,7 +109,13 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": names, "samples": len(self.samples)}
 
 
-def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None):
+def workload_name(dim, edge, world):
+    shape = (edge * world,) + (edge,) * (dim - 1)
+    return (f"{dim}D Q{1 << dim} {edge}^{dim} modal stiffness apply per GPU (BASELINE configs[{dim - 1}]); "
+            f"global grid {'x'.join(map(str, shape))}, one k0 slab per GPU, no comm")
+
+
+def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None, world=1):
     """Times the reference's CPU implementation of the path (oracle/_ref: the
     unmodified reference header in the harness loop, OpenMP over k0 on all host
     threads; the C port if _ref is absent) on a bounded k0-slab sample of the
@@ -118,7 +124,7 @@ def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None):
     impl = oracle.best(fast=True)
     # every host thread the process may use; not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     threads = threads or len(os.sched_getaffinity(0))
-    shape = (edge, edge, edge)
+    shape = (edge * world, edge, edge)               # the same global grid as the GPU arm at this N
     L = tuple(n * h for n, h in zip(shape, SPACING))
     plane = edge * edge
     # calibrate on a few planes, then size the sample for ~target_step_s per step
@@ -141,7 +147,7 @@ def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None):
     dt = (time.perf_counter() - t0) / steps
     modes = planes * plane
     descr = {"value": modes / dt / 1e9, "unit": UNIT, "cores": int(threads), "kind": impl.kind,
-             "sample": f"{planes} of {edge} k0-planes of the {edge}^3 grid ({modes} modes) per step, "
+             "sample": f"{planes} of {shape[0]} k0-planes of the {'x'.join(map(str, shape))} grid ({modes} modes) per step, "
                        f"{steps} steps, -O3 x86-64-v3 OpenMP build of {os.path.basename(impl.path)}"}
     return modes / dt / 1e9, dt, descr
 
@@ -149,14 +155,16 @@ def cpu_reference_leg(edge, steps, warmup, target_step_s, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    workload = (f"3D Q8 {args.edge}^3 modal stiffness apply per GPU (BASELINE configs[2]); "
-                "reference CPU path (tests/test_bri17.cpp:76-91 loop over Hooke::modal_stiffness), host cores only")
+    workload = workload_name(3, args.edge, args.gpus)
     value, dt, descr = cpu_reference_leg(args.edge, max(1, args.steps), max(0, args.warmup),
-                                         target_step_s=0.25)
+                                         target_step_s=0.25, world=args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload, "sample": descr["sample"]},
+            "data": "synthetic",
+            "config": {"workload": workload, "sample": descr["sample"],
+                       "implementation": "reference CPU path: tests/test_bri17.cpp:76-91 loop over the unmodified "
+                                         "Hooke::modal_stiffness (oracle/_ref), OpenMP over k0, host cores only"},
             "cpu_baseline": descr,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -322,9 +330,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{dim}D Q{1 << dim} {edge}^{dim} modal stiffness apply per GPU "
-                                   f"(BASELINE configs[{dim - 1}]); global grid {'x'.join(map(str, shape))}, "
-                                   "one k0 slab per GPU, no comm",
+            "config": {"workload": workload_name(dim, edge, world),
                        "modes_per_gpu": modes_rank, "mu": MU, "nu": NU, "spacing": SPACING,
                        "l2": "inputs (6 GiB) and outputs (6 GiB) per GPU exceed the 126 MB L2; no flush",
                        "kernel_variant": op.info("apply_variant"), "grid": op.info("last_grid"),
