@@ -332,7 +332,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(dim, edge, world),
                        "modes_per_gpu": modes_rank, "mu": MU, "nu": NU, "spacing": SPACING,
-                       "l2": "inputs (6 GiB) and outputs (6 GiB) per GPU exceed the 126 MB L2; no flush",
+                       "l2": f"inputs ({modes_rank * 16 * dim / 2**30:.2f} GiB) and outputs (same) per GPU vs the 126 MB L2: "
+                             + ("far larger, no flush between iterations" if modes_rank * 16 * dim > 2**30
+                                else "NOT larger than L2 (non-default size: timing is L2-assisted)"),
                        "kernel_variant": op.info("apply_variant"), "grid": op.info("last_grid"),
                        "block": op.info("last_block"), "smem": op.info("last_smem")},
             "gdof_per_s": value * dim,
