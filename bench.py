@@ -67,7 +67,7 @@ class ClockSampler:
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
     NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.samples, self.reasons, self.max_mhz = [], 0, None
         self._stop = threading.Event()
         self._thread = None
@@ -75,7 +75,10 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            try:        # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: go by UUID
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # NVML missing: report it, do not fail the bench
             self.nv, self.err = None, repr(e)
@@ -243,7 +246,7 @@ def main():
         op.set_option("apply_variant", args.variant)
 
     launches0 = op.info("launches")
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     ms = timed(lambda: op.apply_modal_stiffness(u, out=f, k_begin=k_begin), args.steps, args.warmup,
                sampler)
     launches = op.info("launches") - launches0 - args.warmup
