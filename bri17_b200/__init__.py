@@ -95,6 +95,23 @@ def _check_contiguous(a, dtype, what):
         raise ValueError(f"expected one-dimensional, contiguous array ({what})")
 
 
+def _freq(k, shape, wrap):
+    """``k`` as the reference's binding takes it: pybind11's ``array_t<int>`` converts any integer
+    sequence (python/pybri17.cpp:76-95) and the C++ methods never bound-check ``k``
+    (bri17.hpp:212,247).  K^ is N-periodic in k (cos/sin of 2 pi k/N), so ``wrap=True`` maps k
+    into [0, N); B^ uses half angles and is NOT N-periodic (k -> k+N flips signs), so it keeps
+    the table range and rejects indices outside [0, N)."""
+    a = np.asarray(k)
+    if a.ndim != 1 or not np.issubdtype(a.dtype, np.integer) and a.dtype != np.bool_:
+        raise ValueError("expected one-dimensional, contiguous array (k)")
+    if a.shape[0] != len(shape):
+        raise ValueError(f"expected {len(shape)} frequency indices")
+    a = a.astype(np.int64)
+    if wrap:
+        a = np.mod(a, np.asarray(shape, dtype=np.int64))
+    return np.ascontiguousarray(a, dtype=np.intc)
+
+
 # ---------------------------------------------------------------------------
 # Hooke -- include/bri17/bri17.hpp:176-356, python/pybri17.cpp:63-96
 # ---------------------------------------------------------------------------
@@ -124,13 +141,13 @@ class _Hooke:
     def modal_stiffness_matrix(self, k, K):
         """Hooke::modal_stiffness (bri17.hpp:247-292) under its Python name
         (python/pybri17.cpp:82): fills ``K`` (dim*dim complex128, row-major)."""
-        _check_contiguous(k, np.dtype(np.intc), "k")
+        k = _freq(k, self.grid.shape, wrap=True)
         _check_contiguous(K, np.dtype(np.complex128), "K")
         check(self._lib.bri17_modal_stiffness_mode_f64(self._plan, _p_i32(k), _p_f64(K)))
 
     def modal_strain_displacement(self, k, B):
         """Hooke::modal_strain_displacement (bri17.hpp:212-236)."""
-        _check_contiguous(k, np.dtype(np.intc), "k")
+        k = _freq(k, self.grid.shape, wrap=False)
         _check_contiguous(B, np.dtype(np.complex128), "B")
         check(self._lib.bri17_modal_strain_displacement_mode_f64(self._plan, _p_i32(k), _p_f64(B)))
 
@@ -138,7 +155,7 @@ class _Hooke:
         """Hooke::modal_eigenstress_to_opposite_strain (bri17.hpp:308-355,
         python/pybri17.cpp:88-95): ``eta`` <- -strain induced by eigenstress ``tau``
         (Mandel notation, 3 or 6 complex128)."""
-        _check_contiguous(k, np.dtype(np.intc), "k")
+        k = _freq(k, self.grid.shape, wrap=False)
         _check_contiguous(tau, np.dtype(np.complex128), "tau")
         _check_contiguous(eta, np.dtype(np.complex128), "eta")
         check(self._lib.bri17_modal_eigenstress_to_opposite_strain_mode_f64(
@@ -169,13 +186,16 @@ class Hooke3f64(_Hooke):
     dim = 3
 
 
-def _dev_ptr(t):
-    """Device pointer of a torch tensor / cuda-array-interface object / int."""
+def _dev_ptr(t, device=None):
+    """Device pointer of a torch tensor / cuda-array-interface object / int; ``device``: the
+    ordinal the tensor must live on (the plan's)."""
     if isinstance(t, int):
         return t
     if hasattr(t, "data_ptr"):
         if not t.is_cuda:
             raise ValueError("expected a CUDA tensor (use the *_host entry point for host memory)")
+        if device is not None and t.device.index != device:
+            raise ValueError(f"tensor lives on {t.device}, the plan on cuda:{device}")
         if not t.is_contiguous():
             raise ValueError("expected a contiguous tensor")
         return t.data_ptr()
@@ -237,9 +257,29 @@ class ModalOperator:
         elif out.shape != u_hat.shape or out.dtype != u_hat.dtype:
             raise ValueError("out must match u_hat")
         check(self._lib.bri17_modal_stiffness_apply_f64(
-            self._plan, _dev_ptr(u_hat), _dev_ptr(out), _p_i32(kb), _p_i32(local), 0,
+            self._plan, _dev_ptr(u_hat, self.device), _dev_ptr(out, self.device), _p_i32(kb), _p_i32(local), 0,
             float(out_scale), _stream_ptr(stream)))
         return out
+
+    def apply_modal_stiffness_dot(self, u_hat, out=None, k_begin=None, out_scale=1.0, hermitian_n=0,
+                                  stream=None):
+        """``(f^, sum_k w_k Re(u^_k^H f^_k))``: the apply plus the Parseval sum of the block
+        (bri17_modal_stiffness_apply_dot_f64; ``hermitian_n`` = full length of the fastest axis
+        when the block is the half spectrum of a real field)."""
+        import torch
+        kb, local = self._block(u_hat.shape, self.dim, k_begin)
+        if u_hat.dtype != torch.complex128:
+            raise ValueError("u_hat must be complex128")
+        if out is None:
+            out = torch.empty_like(u_hat)
+        elif out.shape != u_hat.shape or out.dtype != u_hat.dtype:
+            raise ValueError("out must match u_hat")
+        scratch = torch.empty(1184 + 1, dtype=torch.float64, device=u_hat.device)
+        check(self._lib.bri17_modal_stiffness_apply_dot_f64(
+            self._plan, _dev_ptr(u_hat, self.device), _dev_ptr(out, self.device), _p_i32(kb), _p_i32(local), 0,
+            float(out_scale), int(hermitian_n), scratch.data_ptr(), scratch.data_ptr() + 8, 1184,
+            _stream_ptr(stream)))
+        return out, float(scratch[0].item())
 
     def apply_modal_stiffness_host(self, u_hat, out=None, k_begin=None, out_scale=1.0):
         """Same on host memory (numpy arrays or pinned CPU torch tensors);
@@ -315,11 +355,11 @@ class ModalOperator:
             strides = (0, 1, 0, 1)
         kb = _ints(k_begin if k_begin is not None else (0,) * self.dim, self.dim)
         fn = getattr(self._lib, fn_name)
-        if fn_name == "bri17_eigenstress_to_displacement_f64":
-            rc = fn(self._plan, _dev_ptr(x), _dev_ptr(out), _p_i32(kb), _p_i32(local), *strides,
+        if fn_name in ("bri17_eigenstress_to_displacement_f64", "bri17_eigenstress_to_force_f64"):
+            rc = fn(self._plan, _dev_ptr(x, self.device), _dev_ptr(out, self.device), _p_i32(kb), _p_i32(local), *strides,
                     _stream_ptr(stream))
         else:
-            rc = fn(self._plan, _dev_ptr(x), _dev_ptr(out), _p_i32(kb), _p_i32(local), strides[0],
+            rc = fn(self._plan, _dev_ptr(x, self.device), _dev_ptr(out, self.device), _p_i32(kb), _p_i32(local), strides[0],
                     strides[1], _stream_ptr(stream))
         check(rc)
         return out
@@ -333,6 +373,13 @@ class ModalOperator:
         """u^ = K^-1 (tau^ . conj(B^)) per mode (bri17.hpp:340-341)."""
         nsym = self.dim * (self.dim + 1) // 2
         return self._solve("bri17_eigenstress_to_displacement_f64", tau_hat, nsym, self.dim, k_begin,
+                           mode_major, stream)
+
+    def eigenstress_to_force(self, tau_hat, k_begin=None, mode_major=False, stream=None):
+        """f^ = tau^ . conj(B^) per mode (bri17.hpp:340 without the solve): the modal force of the
+        periodic inclusion problem (python/demo.py:11-23), right-hand side of the CG solve."""
+        nsym = self.dim * (self.dim + 1) // 2
+        return self._solve("bri17_eigenstress_to_force_f64", tau_hat, nsym, self.dim, k_begin,
                            mode_major, stream)
 
     def eigenstress_to_opposite_strain(self, tau_hat, k_begin=None, mode_major=False, stream=None):
@@ -349,10 +396,12 @@ class ModalOperator:
         nsym = self.dim * (self.dim + 1) // 2
         if u_hat.dtype != torch.complex128:
             raise ValueError("u_hat must be complex128")
+        want = (nsym,) + tuple(u_hat.shape[1:])
         if out is None:
-            out = torch.empty((nsym,) + tuple(u_hat.shape[1:]), dtype=u_hat.dtype,
-                              device=u_hat.device)
+            out = torch.empty(want, dtype=u_hat.dtype, device=u_hat.device)
+        elif tuple(out.shape) != want or out.dtype != u_hat.dtype:
+            raise ValueError(f"out must be complex128 {want}")
         check(self._lib.bri17_strain_displacement_apply_f64(
-            self._plan, _dev_ptr(u_hat), _dev_ptr(out), _p_i32(kb), _p_i32(local), 0, 0,
-            float(out_scale), _stream_ptr(stream)))
+            self._plan, _dev_ptr(u_hat, self.device), _dev_ptr(out, self.device), _p_i32(kb), _p_i32(local),
+            0, 0, float(out_scale), _stream_ptr(stream)))
         return out

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libbri17_b200.so")
 
-OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED = range(5)
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED, ERR_BREAKDOWN = range(6)
 
 _i32p = C.POINTER(C.c_int)
 _f64p = C.POINTER(C.c_double)
@@ -43,6 +43,10 @@ SIGNATURES = {
                                                         C.c_int64, C.c_int64, _vp]),
     "bri17_eigenstress_to_opposite_strain_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64,
                                                            C.c_int64, _vp]),
+    "bri17_eigenstress_to_force_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_int64,
+                                                 C.c_int64, C.c_int64, _vp]),
+    "bri17_modal_stiffness_apply_dot_f64": (C.c_int, [_vp, _vp, _vp, _i32p, _i32p, C.c_int64, C.c_double,
+                                                      C.c_int, _vp, _vp, C.c_int, _vp]),
 }
 
 # include/bri17_b200_realspace.h (libbri17_b200_rs.so)
@@ -65,6 +69,11 @@ RS_SIGNATURES = {
     "bri17_cg_solve_f64": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _i32p, _f64p, _vp]),
     "bri17_real_space_apply_real_f64": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bri17_cg_solve_real_f64": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _i32p, _f64p, _vp]),
+    "bri17_rs_plan_get_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
+    "bri17_real_space_apply_dot_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, _f64p, _vp]),
+    "bri17_debug_axis0_fused_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
+                                               C.c_int, _vp, _f64p]),
 }
 
 _lib = None

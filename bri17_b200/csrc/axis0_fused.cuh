@@ -1,0 +1,406 @@
+// axis0_fused.cuh -- ONE kernel for  FFT(axis 0) -> K^ . (.) * |h|/|N| -> inverse FFT(axis 0)
+// on the Fourier-side block X[c][n0][column] of the real-space operator
+// (tests/test_bri17.cpp:57 [axis 0 of the forward transforms], :58-92 [modal loop], :93-106
+// [scale], :95 [axis 0 of the backward transforms] of the reference).
+//
+// Round 1 ran these as three passes over HBM (cuFFT strided Z2Z, modal kernel, cuFFT): 7.4 of the
+// 15.8 ms of a 512^3 apply.  Here a CTA owns a tile of W consecutive columns x all N0 points x all
+// components in shared memory (96 KiB for N0 <= 512, 192 KiB for N0 = 1024), so the block is read
+// once and written once:
+//
+//   global --(stage 0: radix R0 butterflies in registers)--> smem --(stages 1..)--> smem
+//          --(last forward stage, K^ per mode, first inverse stage: same owner thread, no barrier)-->
+//   smem --(inverse stages)--> (last inverse stage stores straight to global, natural order)
+//
+// Forward = decimation in frequency (natural order in, digit-reversed out), inverse = the
+// transposed flow graph with conjugated twiddles (digit-reversed in, natural out): no reordering
+// pass, and K^ is applied in digit-reversed position with k0 recovered from the position's digits.
+// Twiddles exp(-2 pi i j/N0) come from a host-built table staged in shared memory; complex
+// products use explicit fma (the library is compiled with -fmad=false for the bit-exact kernels).
+// The modal arithmetic is the reference's, in its written order (bri17.hpp:266-288).
+//
+// Shared-memory layout: data[c][n][w] (complex), w fastest.  A 128-bit access is served in
+// quarter-warps (8 lanes = 128 B = all banks once).  W >= 8: the 8 lanes are 8 consecutive w of one
+// n -> conflict-free.  W = 4: 8 lanes = 2 butterflies x 4 columns; in the stride-1 stage (radix 8)
+// the two butterflies are 8 rows = 512 B apart -> same banks; rows are therefore stored at
+// n ^ ((n >> 3) & 1), which puts the two rows in different halves of the 128 B line and leaves the
+// other stages' quarter-warps contiguous.
+//
+// Everything below the kernel is __host__ __device__: tests replay the phases thread by thread on
+// the CPU (bri17_debug_axis0_fused_host) against numpy's FFT, so that index arithmetic is checked
+// without a GPU.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+#ifdef __CUDACC__
+#define A0_HD __host__ __device__ __forceinline__
+#else
+#define A0_HD inline
+#endif
+
+namespace bri17b200 {
+namespace axis0 {
+
+struct Params {
+  double2 *X;              // [dim][N0][S], transformed in place
+  long long comp_stride;   // complex elements between components (>= N0*S)
+  long long S;             // columns (complex elements per n0 row)
+  long long n_tiles;       // ceil(S / W)
+  int N0;
+  int S2e;                 // 3-D: extent of the fastest axis in the block (column = b*S2e + k2); 2-D: 1
+  int k1_begin;            // global index of the first k1 (axis-1 frequency) of the block
+  const double *tab0, *tab1, *tab2;  // per-axis phi|chi|psi, [3][N_d] (tab2 unused in 2-D)
+  int N1, N2;              // table lengths of axes 1 and 2
+  const double2 *twiddle;  // exp(-2 pi i j / N0), j < N0
+  double mu, scaling, out_scale;
+  double *dot_partial;     // optional: one partial sum of w_k Re(u^H f) per CTA
+  int herm_n;              // > 0: the fastest axis is the half spectrum of a real field of this length
+};
+
+// ---- complex helpers -------------------------------------------------------
+A0_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+A0_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+A0_HD double fma_(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+// a * (c, s) with s the IMAGINARY part of the factor actually applied
+A0_HD double2 cmul(double2 a, double cr, double ci) {
+  return make_double2(fma_(a.x, cr, -(a.y * ci)), fma_(a.x, ci, a.y * cr));
+}
+// forward: a * (-i); inverse: a * (+i)
+template <bool INV>
+A0_HD double2 rot90(double2 a) {
+  return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+// ---- radix-R DFT in registers, natural order in and out: a[m] <- sum_r a[r] w_R^{+-rm} -------
+template <int R, bool INV>
+struct Dft;
+
+template <bool INV>
+struct Dft<2, INV> {
+  static A0_HD void run(double2 (&a)[2]) {
+    const double2 t = a[0];
+    a[0] = cadd(t, a[1]);
+    a[1] = csub(t, a[1]);
+  }
+};
+
+template <bool INV>
+struct Dft<4, INV> {
+  static A0_HD void run(double2 (&a)[4]) {
+    const double2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+    const double2 t2 = cadd(a[1], a[3]), t3 = rot90<INV>(csub(a[1], a[3]));
+    a[0] = cadd(t0, t2);
+    a[2] = csub(t0, t2);
+    a[1] = cadd(t1, t3);
+    a[3] = csub(t1, t3);
+  }
+};
+
+template <bool INV>
+struct Dft<8, INV> {
+  static A0_HD void run(double2 (&a)[8]) {
+    constexpr double h = 0.70710678118654752440;
+    double2 e[4] = {a[0], a[2], a[4], a[6]}, o[4] = {a[1], a[3], a[5], a[7]};
+    Dft<4, INV>::run(e);
+    Dft<4, INV>::run(o);
+    // o[m] *= w8^{+-m}
+    const double2 o1 = INV ? make_double2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y))
+                           : make_double2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+    const double2 o2 = rot90<INV>(o[2]);
+    const double2 o3 = INV ? make_double2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y))
+                           : make_double2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+    a[0] = cadd(e[0], o[0]); a[4] = csub(e[0], o[0]);
+    a[1] = cadd(e[1], o1);   a[5] = csub(e[1], o1);
+    a[2] = cadd(e[2], o2);   a[6] = csub(e[2], o2);
+    a[3] = cadd(e[3], o3);   a[7] = csub(e[3], o3);
+  }
+};
+
+template <bool INV>
+struct Dft<16, INV> {
+  static A0_HD void run(double2 (&a)[16]) {
+    constexpr double h = 0.70710678118654752440;
+    constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // cos, sin(pi/8)
+    double2 e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { e[i] = a[2 * i]; o[i] = a[2 * i + 1]; }
+    Dft<8, INV>::run(e);
+    Dft<8, INV>::run(o);
+    constexpr double sg = INV ? 1. : -1.;  // sign of the imaginary part of w16^{+-m}
+    o[1] = cmul(o[1], c1, sg * s1);
+    o[2] = cmul(o[2], h, sg * h);
+    o[3] = cmul(o[3], s1, sg * c1);
+    o[4] = rot90<INV>(o[4]);
+    o[5] = cmul(o[5], -s1, sg * c1);
+    o[6] = cmul(o[6], -h, sg * h);
+    o[7] = cmul(o[7], -c1, sg * s1);
+#pragma unroll
+    for (int m = 0; m < 8; m++) { a[m] = cadd(e[m], o[m]); a[m + 8] = csub(e[m], o[m]); }
+  }
+};
+
+// ---- global / shared accessors ----------------------------------------------
+A0_HD double2 ld_stream(const double2 *p) {
+#ifdef __CUDA_ARCH__
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+A0_HD void st_stream(double2 *p, double2 v) {
+#ifdef __CUDA_ARCH__
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+A0_HD double ld_tab(const double *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+template <int W>
+A0_HD int swz(int n) {
+  return W == 4 ? (n ^ ((n >> 3) & 1)) : n;
+}
+
+// Configuration: N0 = R0*R1*R2 (R2 = 1: two stages), W columns per tile.
+template <int N0_, int W_, int R0_, int R1_, int R2_>
+struct Cfg {
+  static constexpr int N0 = N0_, W = W_, R0 = R0_, R1 = R1_, R2 = R2_;
+  static constexpr int NS = R2_ == 1 ? 2 : 3;
+  static constexpr int RL = NS == 3 ? R2_ : R1_;            // radix of the last (stride-1) stage
+  static constexpr int NPH = 2 * NS - 1;                    // phases separated by CTA barriers
+  static constexpr int THREADS = 256;
+  static constexpr int MINB = (N0_ * W_ * 3 * 16 + N0_ * 16) <= 110 * 1024 ? 2 : 1;
+  static constexpr size_t smem_bytes(int dim) { return size_t(N0_) * 16 + size_t(dim) * N0_ * W_ * 16; }
+  static_assert(R0_ * R1_ * R2_ == N0_, "radices must multiply to N0");
+  static_assert(RL == 8, "the stride-1 stage must be radix 8 (bank swizzle)");
+  static_assert(W_ % 4 == 0 && THREADS % W_ == 0, "W must divide the CTA size");
+};
+
+// ---- forward stage (not the last one): radix R on sub-blocks of size BS -----------------
+template <class C, int DIM, int R, int BS, bool FIRST>
+A0_HD void fwd_stage(int tid, double2 *data, const double2 *tw, const Params &p, long long col0) {
+  constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R, twstep = N0 / BS;
+  for (int item = tid; item < nbf * W; item += C::THREADS) {
+    const int w = item % W, q = item / W;
+    if (col0 + w >= p.S) continue;
+    const int blk = q / stride, j = q % stride;
+    const int nb = blk * BS + j;
+#pragma unroll 1
+    for (int c = 0; c < DIM; c++) {
+      double2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int n = nb + r * stride;
+        a[r] = FIRST ? ld_stream(p.X + c * p.comp_stride + (long long)n * p.S + col0 + w)
+                     : data[(c * N0 + swz<W>(n)) * W + w];
+      }
+      Dft<R, false>::run(a);
+#pragma unroll
+      for (int m = 1; m < R; m++) {
+        const double2 t = tw[j * m * twstep];
+        a[m] = cmul(a[m], t.x, t.y);
+      }
+#pragma unroll
+      for (int m = 0; m < R; m++) data[(c * N0 + swz<W>(nb + m * stride)) * W + w] = a[m];
+    }
+  }
+}
+
+// ---- inverse stage (not the first one): transposed forward stage, conjugated twiddles --------
+template <class C, int DIM, int R, int BS, bool LAST>
+A0_HD void inv_stage(int tid, double2 *data, const double2 *tw, const Params &p, long long col0) {
+  constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R, twstep = N0 / BS;
+  for (int item = tid; item < nbf * W; item += C::THREADS) {
+    const int w = item % W, q = item / W;
+    if (col0 + w >= p.S) continue;
+    const int blk = q / stride, j = q % stride;
+    const int nb = blk * BS + j;
+#pragma unroll 1
+    for (int c = 0; c < DIM; c++) {
+      double2 a[R];
+#pragma unroll
+      for (int m = 0; m < R; m++) a[m] = data[(c * N0 + swz<W>(nb + m * stride)) * W + w];
+#pragma unroll
+      for (int m = 1; m < R; m++) {
+        const double2 t = tw[j * m * twstep];
+        a[m] = cmul(a[m], t.x, -t.y);
+      }
+      Dft<R, true>::run(a);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int n = nb + r * stride;
+        if (LAST) st_stream(p.X + c * p.comp_stride + (long long)n * p.S + col0 + w, a[r]);
+        else data[(c * N0 + swz<W>(n)) * W + w] = a[r];
+      }
+    }
+  }
+}
+
+// K^ u of one mode from the per-axis factors, the reference's operation order
+// (bri17.hpp:268-274 / :276-288; product tests/test_bri17.cpp:68 / :84, left to right).
+template <int DIM>
+A0_HD void stiffness_times(const double *phi, const double *chi, const double *psi, double mu, double scaling,
+                           const double2 *u, double2 *f) {
+  if constexpr (DIM == 3) {
+    const double H00 = (phi[0] * chi[1]) * chi[2];
+    const double H11 = (chi[0] * phi[1]) * chi[2];
+    const double H22 = (chi[0] * chi[1]) * phi[2];
+    const double Kd = mu * ((H00 + H11) + H22);
+    const double K00 = scaling * H00 + Kd, K11 = scaling * H11 + Kd, K22 = scaling * H22 + Kd;
+    const double K01 = ((scaling * psi[0]) * psi[1]) * chi[2];
+    const double K02 = ((scaling * psi[0]) * chi[1]) * psi[2];
+    const double K12 = ((scaling * chi[0]) * psi[1]) * psi[2];
+    f[0] = make_double2((K00 * u[0].x + K01 * u[1].x) + K02 * u[2].x, (K00 * u[0].y + K01 * u[1].y) + K02 * u[2].y);
+    f[1] = make_double2((K01 * u[0].x + K11 * u[1].x) + K12 * u[2].x, (K01 * u[0].y + K11 * u[1].y) + K12 * u[2].y);
+    f[2] = make_double2((K02 * u[0].x + K12 * u[1].x) + K22 * u[2].x, (K02 * u[0].y + K12 * u[1].y) + K22 * u[2].y);
+  } else {
+    const double H00 = phi[0] * chi[1];
+    const double H11 = chi[0] * phi[1];
+    const double Kd = mu * (H00 + H11);
+    const double K00 = scaling * H00 + Kd, K11 = scaling * H11 + Kd;
+    const double K01 = (scaling * psi[0]) * psi[1];
+    f[0] = make_double2(K00 * u[0].x + K01 * u[1].x, K00 * u[0].y + K01 * u[1].y);
+    f[1] = make_double2(K01 * u[0].x + K11 * u[1].x, K01 * u[0].y + K11 * u[1].y);
+  }
+}
+
+// ---- middle phase: last forward stage (stride 1), K^ in digit-reversed position, first inverse
+// stage.  The same thread owns the RL positions q*RL .. q*RL+RL-1 of its column in all three
+// steps, so no CTA barrier is needed between them. --------------------------------------------
+template <class C, int DIM>
+A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, double &dot_acc) {
+  constexpr int N0 = C::N0, W = C::W, R = C::RL, nbf = N0 / R;
+  for (int item = tid; item < nbf * W; item += C::THREADS) {
+    const int w = item % W, q = item / W;
+    const long long col = col0 + w;
+    if (col >= p.S) continue;
+    const int nb = q * R;
+#pragma unroll 1
+    for (int c = 0; c < DIM; c++) {  // last forward stage: no twiddle after it
+      double2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) a[r] = data[(c * N0 + swz<W>(nb + r)) * W + w];
+      Dft<R, false>::run(a);
+#pragma unroll
+      for (int r = 0; r < R; r++) data[(c * N0 + swz<W>(nb + r)) * W + w] = a[r];
+    }
+    // position nb + r holds frequency k0 = kbase + r * (N0 / R): digits of q, least significant
+    // stage first (decimation in frequency leaves the spectrum in digit-reversed order)
+    int kbase;
+    if constexpr (C::NS == 3) kbase = q / C::R1 + C::R0 * (q % C::R1);
+    else kbase = q;
+    double phi[3], chi[3], psi[3];
+    int k_last;
+    if constexpr (DIM == 3) {
+      const int b = int(col / p.S2e), k2 = int(col - (long long)b * p.S2e), k1 = p.k1_begin + b;
+      phi[1] = ld_tab(p.tab1 + k1); chi[1] = ld_tab(p.tab1 + p.N1 + k1); psi[1] = ld_tab(p.tab1 + 2 * p.N1 + k1);
+      phi[2] = ld_tab(p.tab2 + k2); chi[2] = ld_tab(p.tab2 + p.N2 + k2); psi[2] = ld_tab(p.tab2 + 2 * p.N2 + k2);
+      k_last = k2;
+    } else {
+      const int k1 = p.k1_begin + int(col);
+      phi[1] = ld_tab(p.tab1 + k1); chi[1] = ld_tab(p.tab1 + p.N1 + k1); psi[1] = ld_tab(p.tab1 + 2 * p.N1 + k1);
+      k_last = k1;
+    }
+    const double wgt = (p.herm_n > 0 && k_last != 0 && 2 * k_last != p.herm_n) ? 2. : 1.;
+#pragma unroll 2
+    for (int r = 0; r < R; r++) {
+      const int k0 = kbase + r * nbf;
+      phi[0] = ld_tab(p.tab0 + k0); chi[0] = ld_tab(p.tab0 + N0 + k0); psi[0] = ld_tab(p.tab0 + 2 * N0 + k0);
+      double2 u[DIM], f[DIM];
+#pragma unroll
+      for (int c = 0; c < DIM; c++) u[c] = data[(c * N0 + swz<W>(nb + r)) * W + w];
+      stiffness_times<DIM>(phi, chi, psi, p.mu, p.scaling, u, f);
+#pragma unroll
+      for (int c = 0; c < DIM; c++) {
+        f[c].x *= p.out_scale; f[c].y *= p.out_scale;
+        data[(c * N0 + swz<W>(nb + r)) * W + w] = f[c];
+      }
+      if (p.dot_partial) {
+        double d = u[0].x * f[0].x + u[0].y * f[0].y;
+#pragma unroll
+        for (int c = 1; c < DIM; c++) d += u[c].x * f[c].x + u[c].y * f[c].y;
+        dot_acc += wgt * d;
+      }
+    }
+#pragma unroll 1
+    for (int c = 0; c < DIM; c++) {  // first inverse stage (stride 1): no twiddle before it
+      double2 a[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) a[r] = data[(c * N0 + swz<W>(nb + r)) * W + w];
+      Dft<R, true>::run(a);
+#pragma unroll
+      for (int r = 0; r < R; r++) data[(c * N0 + swz<W>(nb + r)) * W + w] = a[r];
+    }
+  }
+}
+
+// Phase PH of a tile for thread `tid`; a CTA barrier separates consecutive phases.
+template <class C, int DIM, int PH>
+A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, double &dot_acc) {
+  if constexpr (C::NS == 3) {
+    if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+    else if constexpr (PH == 1) fwd_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw, p, col0);
+    else if constexpr (PH == 2) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
+    else if constexpr (PH == 3) inv_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw, p, col0);
+    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+  } else {
+    if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+    else if constexpr (PH == 1) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
+    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+  }
+}
+
+// CPU replay of the kernel, thread by thread (tests only; a barrier = the end of a tid loop).
+template <class C, int DIM>
+void emulate_host(const Params &p, double *dot_out) {
+  double2 *data = new double2[size_t(DIM) * C::N0 * C::W];
+  double *acc = new double[C::THREADS]();
+  for (long long tile = 0; tile < p.n_tiles; tile++) {
+    const long long col0 = tile * C::W;
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, acc[t]);
+    if constexpr (C::NPH > 3) {
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, acc[t]);
+    }
+  }
+  if (dot_out) {
+    double s = 0.;
+    for (int t = 0; t < C::THREADS; t++) s += acc[t];
+    *dot_out = s;
+  }
+  delete[] data;
+  delete[] acc;
+}
+
+// Supported axis-0 lengths and their factorizations.
+using Cfg16 = Cfg<16, 128, 2, 8, 1>;
+using Cfg32 = Cfg<32, 64, 4, 8, 1>;
+using Cfg64 = Cfg<64, 32, 8, 8, 1>;
+using Cfg128 = Cfg<128, 16, 2, 8, 8>;
+using Cfg256 = Cfg<256, 8, 4, 8, 8>;
+using Cfg512 = Cfg<512, 4, 8, 8, 8>;
+using Cfg1024 = Cfg<1024, 4, 16, 8, 8>;
+
+inline bool supported(int N0) {
+  return N0 == 16 || N0 == 32 || N0 == 64 || N0 == 128 || N0 == 256 || N0 == 512 || N0 == 1024;
+}
+
+}  // namespace axis0
+}  // namespace bri17b200

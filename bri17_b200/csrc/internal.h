@@ -3,7 +3,9 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -24,9 +26,11 @@ int fail(int code, const std::string &msg);
   } while (0)
 
 // ---- per-axis tables ----------------------------------------------------------
-// Device layout of one axis: six arrays of N doubles, back to back:
-//   phi | chi | psi | c | s | alpha   (bri17.hpp:261-263, :220-221 and :218)
-enum { TAB_PHI = 0, TAB_CHI = 1, TAB_PSI = 2, TAB_C = 3, TAB_S = 4, TAB_ALPHA = 5, TAB_COUNT = 6 };
+// Device layout of one axis: seven arrays of N doubles, back to back:
+//   phi | chi | psi | c | s | alpha | sin(alpha)   (bri17.hpp:261-263, :220-221 and :218)
+// sin(alpha) (unscaled, unlike s = sin(alpha)*N/L) lets the device build the prefactor
+// e^{i sum(alpha)} of B^ (:224) as a product of per-axis (cos, sin) pairs instead of a sincos.
+enum { TAB_PHI = 0, TAB_CHI = 1, TAB_PSI = 2, TAB_C = 3, TAB_S = 4, TAB_ALPHA = 5, TAB_SINA = 6, TAB_COUNT = 7 };
 
 struct AxisTables {
   std::vector<double> host;  // TAB_COUNT * n
@@ -75,6 +79,10 @@ struct ApplyParams {
   int N_outer, N_mid, N_inner;  // table lengths (global shape)
   double mu, scaling, out_scale;
   int stage_outer;      // outer/mid tables of the local range are staged in smem
+  // dot variant of the flat kernel only: per-CTA partial sums of w_k Re(u^_k^H f^_k)
+  double *dot_partial;
+  int herm_n;           // > 0: the fastest axis is the half spectrum of a real field of this
+                        // length; modes with 0 < k < N/2 stand for a conjugate pair (w_k = 2)
 };
 
 struct Variant {
@@ -99,7 +107,6 @@ struct bri17_plan {
   bri17b200::AxisTables tab[3];
   int apply_variant = -1;  // -1: default
   int mapping = 0;         // 0 auto, 1 always row tiles, 2 always flat tiles
-  int last_flat = 0;
   int64_t host_chunk_rows = 0;
   int host_streams = 3;
   int host_zero_copy = 0;  // 1: kernels access pinned host memory directly (no staging)
@@ -110,7 +117,10 @@ struct bri17_plan {
   };
   std::vector<HostStage> stages;
   int64_t stage_bytes = 0;
-  int64_t last_grid = 0, last_block = 0, last_smem = 0, launches = 0;
+  std::mutex host_mutex;   // the staging set is shared: host-buffer calls on one plan are serialised
+  // diagnostics only (bri17_plan_get_info); atomics so that concurrent launches on one plan do not race
+  std::atomic<int64_t> last_grid{0}, last_block{0}, last_smem{0}, launches{0};
+  std::atomic<int> last_flat{0};
 };
 
 namespace bri17b200 {
@@ -128,7 +138,11 @@ int launch_strain_field(bri17_plan *p, const Block &b, void *B, cudaStream_t str
 int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
                         int64_t u_stride, int64_t e_stride, double out_scale,
                         cudaStream_t stream);
-// mode: 0 u^ = K^-1 f^; 1 u^ = K^-1 (tau^ . conj B^); 2 eta^ = sym(B^ (x) u^) of mode 1
+int launch_apply_dot(bri17_plan *p, const Block &b, const void *u, void *f, int64_t u_stride,
+                     int64_t f_stride, double out_scale, int herm_n, double *dot_out, double *scratch,
+                     int scratch_count, cudaStream_t stream);
+// mode: 0 u^ = K^-1 f^; 1 u^ = K^-1 (tau^ . conj B^); 2 eta^ = sym(B^ (x) u^) of mode 1;
+//       3 f^ = tau^ . conj B^ (no solve: the right-hand side of mode 1, bri17.hpp:340)
 int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, void *out,
                        int64_t in_cs, int64_t in_ms, int64_t out_cs, int64_t out_ms, cudaStream_t stream);
 int walk_tiles_host(const Block &b, int tile_modes, int max_ctas, int cta, int64_t *out, int cap, int *grid_out);

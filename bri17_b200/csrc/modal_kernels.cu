@@ -267,6 +267,27 @@ struct FlatIndex {
   long long i;
   int a, b, col;
 };
+
+// Weight of frequency k of the fastest axis in a sum over the FULL spectrum when only the half
+// spectrum k <= N/2 of a real field is stored: k and N-k are a conjugate pair except k = 0 and
+// k = N/2 (even N).  herm_n = 0: the axis is complete, every mode counts once.
+__device__ __forceinline__ double pair_weight(int herm_n, int k) {
+  return (herm_n > 0 && k != 0 && 2 * k != herm_n) ? 2. : 1.;
+}
+
+// Sum over the CTA, valid in thread 0 (fixed order: deterministic).
+template <int THREADS>
+__device__ __forceinline__ double cta_sum(double v) {
+  __shared__ double sh[THREADS / 32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.;
+  if (threadIdx.x < THREADS / 32) t = sh[threadIdx.x];
+  if (threadIdx.x < 32)
+    for (int o = THREADS / 64; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
 __device__ __forceinline__ FlatIndex flat_index(const TileGeom &g, long long i) {
   FlatIndex f;
   f.i = i;
@@ -284,9 +305,13 @@ __device__ __forceinline__ FlatIndex flat_index(const TileGeom &g, long long i) 
   return f;
 }
 
-template <int DIM, int THREADS, int VEC, int MINB>
+// DOT: also accumulates sum_k w_k Re(u^_k^H f^_k) (f^ including out_scale) into one partial sum per
+// CTA -- by Parseval this is |N| <u, F> of the real-space fields, which lets CG take <p, A p> from
+// the operator application itself instead of a separate pass over both vectors.
+template <int DIM, int THREADS, int VEC, int MINB, bool DOT>
 __global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_flat_kernel(const ApplyParams p) {
   extern __shared__ double smem[];
+  double dot_acc = 0.;
   constexpr int TILE = THREADS * VEC;
   const TileGeom &g = p.g;
   // tables of the local ranges: outer | mid | inner, each [phi|chi|psi]
@@ -369,6 +394,10 @@ __global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_flat_kern
         __stcs(o, f0);
         __stcs(o + p.f_stride, f1);
         __stcs(o + 2 * p.f_stride, f2);
+        if constexpr (DOT) {
+          const double w = pair_weight(p.herm_n, g.kb_inner + f[j].col);
+          dot_acc += w * (u0.x * f0.x + u0.y * f0.y + u1.x * f1.x + u1.y * f1.y + u2.x * f2.x + u2.y * f2.y);
+        }
       } else {
         const double H00 = mul(p0, cI);                          // :268
         const double H11 = mul(c0, pI);                          // :269
@@ -388,9 +417,25 @@ __global__ void __launch_bounds__(THREADS, MINB) modal_stiffness_apply_flat_kern
         }
         __stcs(o, f0);
         __stcs(o + p.f_stride, f1);
+        if constexpr (DOT) {
+          const double w = pair_weight(p.herm_n, g.kb_inner + f[j].col);
+          dot_acc += w * (u0.x * f0.x + u0.y * f0.y + u1.x * f1.x + u1.y * f1.y);
+        }
       }
     }
   }
+  if constexpr (DOT) {
+    dot_acc = cta_sum<THREADS>(dot_acc);
+    if (threadIdx.x == 0) p.dot_partial[blockIdx.x] = dot_acc;
+  }
+}
+
+// partial[0..n) -> *out, one CTA, fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) dot_finish_kernel(const double *partial, int n, double *out) {
+  double acc = 0.;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  acc = cta_sum<256>(acc);
+  if (threadIdx.x == 0) *out = acc;
 }
 
 // K6, flat mapping
@@ -437,91 +482,41 @@ __global__ void __launch_bounds__(256) freq_index_map_kernel(const TileGeom g, i
 }
 
 // ---------------------------------------------------------------------------
-// K^ field (diagnostic): what a loop over Hooke::modal_stiffness would write
-// ---------------------------------------------------------------------------
-template <int DIM>
-__global__ void __launch_bounds__(256) modal_stiffness_field_kernel(const ApplyParams p) {
-  constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
-  const TileGeom &g = p.g;
-  const double mu = p.mu, scaling = p.scaling;
-  double2 *K = p.f;
-  TileCursor cur;
-  for (cur.init(g, blockIdx.x); cur.valid(g); cur.next(g, gridDim.x)) {
-    const long long base = cur.row * g.n_inner;
-    const int ka = g.kb_outer + cur.a;
-    const double p0 = __ldg(p.tab_outer + ka), c0 = __ldg(p.tab_outer + p.N_outer + ka),
-                 s0 = __ldg(p.tab_outer + 2 * size_t(p.N_outer) + ka);
-#pragma unroll
-    for (int j = 0; j < VEC; j++) {
-      const int col = cur.chunk * TILE + j * THREADS + threadIdx.x;
-      if (col >= g.n_inner) continue;
-      const int ki = g.kb_inner + col;
-      const double pI = __ldg(p.tab_inner + ki), cI = __ldg(p.tab_inner + p.N_inner + ki),
-                   sI = __ldg(p.tab_inner + 2 * size_t(p.N_inner) + ki);
-      double2 *o = K + (base + col) * (DIM * DIM);
-      if constexpr (DIM == 3) {
-        const int kb = g.kb_mid + cur.b;
-        const double p1 = __ldg(p.tab_mid + kb), c1 = __ldg(p.tab_mid + p.N_mid + kb),
-                     s1 = __ldg(p.tab_mid + 2 * size_t(p.N_mid) + kb);
-        const double H00 = mul(mul(p0, c1), cI);
-        const double H11 = mul(mul(c0, p1), cI);
-        const double H22 = mul(mul(c0, c1), pI);
-        const double Kd = mul(mu, add(add(H00, H11), H22));
-        const double K00 = add(mul(scaling, H00), Kd);
-        const double K01 = mul(mul(mul(scaling, s0), s1), cI);
-        const double K02 = mul(mul(mul(scaling, s0), c1), sI);
-        const double K11 = add(mul(scaling, H11), Kd);
-        const double K12 = mul(mul(mul(scaling, c0), s1), sI);
-        const double K22 = add(mul(scaling, H22), Kd);
-        o[0] = make_double2(K00, 0.); o[1] = make_double2(K01, 0.); o[2] = make_double2(K02, 0.);
-        o[3] = make_double2(K01, 0.); o[4] = make_double2(K11, 0.); o[5] = make_double2(K12, 0.);
-        o[6] = make_double2(K02, 0.); o[7] = make_double2(K12, 0.); o[8] = make_double2(K22, 0.);
-      } else {
-        const double H00 = mul(p0, cI);
-        const double H11 = mul(c0, pI);
-        const double Kd = mul(mu, add(H00, H11));
-        const double K00 = add(mul(scaling, H00), Kd);
-        const double K01 = mul(mul(scaling, s0), sI);
-        const double K11 = add(mul(scaling, H11), Kd);
-        o[0] = make_double2(K00, 0.); o[1] = make_double2(K01, 0.);
-        o[2] = make_double2(K01, 0.); o[3] = make_double2(K11, 0.);
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // K3: strain-displacement.  B^_i = prefactor * s_i * prod_{j != i} c_j with
 // prefactor = (-2 sin S, 2 cos S), S = sum of the half angles (bri17.hpp:224).
-// c/s come from the host tables; sin S / cos S are evaluated with the device
-// sincos on the reference's own argument (the fp64 sum of (pi*k_i)/N_i in the
-// reference's order), the only transcendental evaluated on the GPU.  It is
-// well conditioned (absolute error <= 2 ulp of 1), unlike 1-cos(beta).
+// c/s come from the host tables.  sin S / cos S are NOT evaluated with a device
+// sincos (a ~100-instruction fp64 software sequence that made these kernels
+// FP64-bound in round 1): e^{iS} = prod_d (cos a_d + i sin a_d) with both factors
+// of every axis taken from the host tables, two complex products per mode.  Each
+// table entry is correctly rounded libm output, so cos S / sin S carry an absolute
+// error of a few ulp of 1 -- the same as a device sincos -- and B^ / eps^ agree with
+// the reference to <= 1e-12 per mode (max-norm), not bitwise.
 // ---------------------------------------------------------------------------
-// Half-angle factors of one grid line: c = cos(alpha), s = sin(alpha)*N/L, alpha = (pi*k)/N,
-// all three from the host tables (bri17.hpp:218-221).
+// Half-angle factors of one grid line: c = cos(alpha), s = sin(alpha)*N/L, sa = sin(alpha),
+// alpha = (pi*k)/N, all three from the host tables (bri17.hpp:218-221).
 struct HalfAngle {
-  double c, s, alpha;
+  double c, s, sa;
 };
 __device__ __forceinline__ HalfAngle half_angle(const double *tab, int N, int k) {
   HalfAngle h;
   h.c = __ldg(tab + size_t(TAB_C) * N + k);
   h.s = __ldg(tab + size_t(TAB_S) * N + k);
-  h.alpha = __ldg(tab + size_t(TAB_ALPHA) * N + k);
+  h.sa = __ldg(tab + size_t(TAB_SINA) * N + k);
   return h;
 }
 
-// B^ of one mode from the per-axis factors (bri17.hpp:224-232).
+// (cos, sin) of the sum of two angles from their (cos, sin) pairs.
+__device__ __forceinline__ double2 rot_mul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// B^ of one mode from the per-axis factors (bri17.hpp:224-232); e_row = (cos, sin) of the
+// sum of the half angles of the slower axes (1, 0 when there is none).
 template <int DIM>
 __device__ __forceinline__ void modal_B(const HalfAngle &h0, const HalfAngle &h1, const HalfAngle &hI,
-                                        double2 *B) {
-  // sum_alpha accumulates in axis order starting from 0 (:215-219)
-  double sum_alpha = h0.alpha;
-  if constexpr (DIM == 3) sum_alpha = add(sum_alpha, h1.alpha);
-  sum_alpha = add(sum_alpha, hI.alpha);
-  double sn, cs;
-  sincos(sum_alpha, &sn, &cs);
-  const double pre_re = mul(-2., sn), pre_im = mul(2., cs);  // :224
+                                        double2 e_row, double2 *B) {
+  const double2 e = rot_mul(e_row, make_double2(hI.c, hI.sa));
+  const double pre_re = mul(-2., e.y), pre_im = mul(2., e.x);  // :224
   if constexpr (DIM == 3) {
     B[0] = make_double2(mul(mul(mul(pre_re, h0.s), h1.c), hI.c), mul(mul(mul(pre_im, h0.s), h1.c), hI.c));
     B[1] = make_double2(mul(mul(mul(pre_re, h0.c), h1.s), hI.c), mul(mul(mul(pre_im, h0.c), h1.s), hI.c));
@@ -536,10 +531,84 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(add(mul(a.x, b.x), -mul(a.y, b.y)), add(mul(a.x, b.y), mul(a.y, b.x)));
 }
 
-// MODE 0: write B^ (mode-major).  MODE 1: eps^ = sym(B^ (x) u^), planar Mandel.
+// ---------------------------------------------------------------------------
+// Mode-major field writers: what a loop over Hooke::modal_strain_displacement (WHAT 0,
+// DIM complex per mode) or Hooke::modal_stiffness (WHAT 1, DIM*DIM complex per mode,
+// diagnostic) would write.  A tile is 256 consecutive modes of a row, one per thread; its
+// output is ONE contiguous run of 256*NC complex numbers, so the values are staged in shared
+// memory and written out with fully coalesced 16-byte stores (round 1 stored 48-144 B per
+// lane with a stride: 0.19-0.48 of the HBM roofline).
+// ---------------------------------------------------------------------------
+template <int DIM, int WHAT>
+__global__ void __launch_bounds__(256) modal_field_kernel(const ApplyParams p) {
+  constexpr int THREADS = 256, TILE = THREADS;
+  constexpr int NC = WHAT == 0 ? DIM : DIM * DIM;
+  __shared__ double2 stage[TILE * NC];  // 3-D K^: 36 KiB
+  const TileGeom &g = p.g;
+  const double mu = p.mu, scaling = p.scaling;
+  TileCursor cur;
+  for (cur.init(g, blockIdx.x); cur.valid(g); cur.next(g, gridDim.x)) {
+    const int col0 = cur.chunk * TILE;
+    const int valid = min(TILE, g.n_inner - col0);
+    if (int(threadIdx.x) < valid) {
+      const int ka = g.kb_outer + cur.a, kb = g.kb_mid + cur.b, ki = g.kb_inner + col0 + threadIdx.x;
+      double2 *o = stage + threadIdx.x * NC;
+      if constexpr (WHAT == 0) {
+        const HalfAngle h0 = half_angle(p.tab_outer, p.N_outer, ka);
+        HalfAngle h1 = h0;
+        double2 e_row = make_double2(h0.c, h0.sa);
+        if constexpr (DIM == 3) {
+          h1 = half_angle(p.tab_mid, p.N_mid, kb);
+          e_row = rot_mul(e_row, make_double2(h1.c, h1.sa));
+        }
+        double2 B[DIM];
+        modal_B<DIM>(h0, h1, half_angle(p.tab_inner, p.N_inner, ki), e_row, B);
+#pragma unroll
+        for (int c = 0; c < DIM; c++) o[c] = B[c];
+      } else {
+        const double p0 = __ldg(p.tab_outer + ka), c0 = __ldg(p.tab_outer + p.N_outer + ka),
+                     s0 = __ldg(p.tab_outer + 2 * size_t(p.N_outer) + ka);
+        const double pI = __ldg(p.tab_inner + ki), cI = __ldg(p.tab_inner + p.N_inner + ki),
+                     sI = __ldg(p.tab_inner + 2 * size_t(p.N_inner) + ki);
+        if constexpr (DIM == 3) {
+          const double p1 = __ldg(p.tab_mid + kb), c1 = __ldg(p.tab_mid + p.N_mid + kb),
+                       s1 = __ldg(p.tab_mid + 2 * size_t(p.N_mid) + kb);
+          const double H00 = mul(mul(p0, c1), cI);
+          const double H11 = mul(mul(c0, p1), cI);
+          const double H22 = mul(mul(c0, c1), pI);
+          const double Kd = mul(mu, add(add(H00, H11), H22));
+          const double K00 = add(mul(scaling, H00), Kd);
+          const double K01 = mul(mul(mul(scaling, s0), s1), cI);
+          const double K02 = mul(mul(mul(scaling, s0), c1), sI);
+          const double K11 = add(mul(scaling, H11), Kd);
+          const double K12 = mul(mul(mul(scaling, c0), s1), sI);
+          const double K22 = add(mul(scaling, H22), Kd);
+          o[0] = make_double2(K00, 0.); o[1] = make_double2(K01, 0.); o[2] = make_double2(K02, 0.);
+          o[3] = make_double2(K01, 0.); o[4] = make_double2(K11, 0.); o[5] = make_double2(K12, 0.);
+          o[6] = make_double2(K02, 0.); o[7] = make_double2(K12, 0.); o[8] = make_double2(K22, 0.);
+        } else {
+          const double H00 = mul(p0, cI);
+          const double H11 = mul(c0, pI);
+          const double Kd = mul(mu, add(H00, H11));
+          const double K00 = add(mul(scaling, H00), Kd);
+          const double K01 = mul(mul(scaling, s0), sI);
+          const double K11 = add(mul(scaling, H11), Kd);
+          o[0] = make_double2(K00, 0.); o[1] = make_double2(K01, 0.);
+          o[2] = make_double2(K01, 0.); o[3] = make_double2(K11, 0.);
+        }
+      }
+    }
+    __syncthreads();
+    double2 *out = p.f + (cur.row * g.n_inner + col0) * NC;
+    for (int i = threadIdx.x; i < valid * NC; i += THREADS) __stcs(out + i, stage[i]);
+    __syncthreads();
+  }
+}
+
+// eps^ = sym(B^ (x) u^), planar Mandel (tests/test_bri17.cpp:194-235).
 // Same persistent-CTA structure as the stiffness apply: the fastest-axis
 // factors of a thread's columns stay in registers from row to row.
-template <int DIM, int MODE>
+template <int DIM>
 __global__ void __launch_bounds__(256, 2) strain_displacement_kernel(const ApplyParams p) {
   constexpr int THREADS = 256, VEC = 2, TILE = THREADS * VEC;
   constexpr int NSYM = DIM * (DIM + 1) / 2;
@@ -562,48 +631,44 @@ __global__ void __launch_bounds__(256, 2) strain_displacement_kernel(const Apply
     }
     const long long base = cur.row * g.n_inner;
     double2 u[VEC][DIM];
-    if constexpr (MODE == 1) {
 #pragma unroll
-      for (int j = 0; j < VEC; j++)
+    for (int j = 0; j < VEC; j++)
 #pragma unroll
-        for (int c = 0; c < DIM; c++)
-          if (ok[j]) u[j][c] = __ldcs(p.u + c * p.u_stride + base + col[j]);
-    }
+      for (int c = 0; c < DIM; c++)
+        if (ok[j]) u[j][c] = __ldcs(p.u + c * p.u_stride + base + col[j]);
     const HalfAngle h0 = half_angle(p.tab_outer, p.N_outer, g.kb_outer + cur.a);
     HalfAngle h1 = h0;
-    if constexpr (DIM == 3) h1 = half_angle(p.tab_mid, p.N_mid, g.kb_mid + cur.b);
+    double2 e_row = make_double2(h0.c, h0.sa);
+    if constexpr (DIM == 3) {
+      h1 = half_angle(p.tab_mid, p.N_mid, g.kb_mid + cur.b);
+      e_row = rot_mul(e_row, make_double2(h1.c, h1.sa));
+    }
 #pragma unroll
     for (int j = 0; j < VEC; j++) {
       if (!ok[j]) continue;
       double2 B[DIM];
-      modal_B<DIM>(h0, h1, hI[j], B);
-      if constexpr (MODE == 0) {
-        double2 *o = p.f + (base + col[j]) * DIM;
+      modal_B<DIM>(h0, h1, hI[j], e_row, B);
+      // Mandel order: tests/test_bri17.cpp:207-209 (2-D), :224-230 (3-D)
+      constexpr int P3[6] = {0, 1, 2, 1, 2, 0}, Q3[6] = {0, 1, 2, 2, 0, 1};
+      constexpr int P2[3] = {0, 1, 0}, Q2[3] = {0, 1, 1};
+      // sqrt(2)*(0.5*x) == (sqrt(2)/2)*x bit for bit: halving is exact
+      const double half_sqrt2 = 0.5 * 1.4142135623730951;
+      double2 *o = p.f + base + col[j];
 #pragma unroll
-        for (int c = 0; c < DIM; c++) o[c] = B[c];
-      } else {
-        // Mandel order: tests/test_bri17.cpp:207-209 (2-D), :224-230 (3-D)
-        constexpr int P3[6] = {0, 1, 2, 1, 2, 0}, Q3[6] = {0, 1, 2, 2, 0, 1};
-        constexpr int P2[3] = {0, 1, 0}, Q2[3] = {0, 1, 1};
-        // sqrt(2)*(0.5*x) == (sqrt(2)/2)*x bit for bit: halving is exact
-        const double half_sqrt2 = 0.5 * 1.4142135623730951;
-        double2 *o = p.f + base + col[j];
-#pragma unroll
-        for (int s = 0; s < NSYM; s++) {
-          const int pp = DIM == 3 ? P3[s] : P2[s], qq = DIM == 3 ? Q3[s] : Q2[s];
-          double2 e;
-          if (pp == qq) {
-            // 0.5*(B_p u_p + u_p B_p): both products are bit-identical, so the sum is an
-            // exact doubling and the half undoes it exactly (:206, :223)
-            e = cmul(B[pp], u[j][pp]);
-          } else {
-            const double2 t1 = cmul(B[pp], u[j][qq]);
-            const double2 t2 = cmul(u[j][pp], B[qq]);
-            e = make_double2(mul(half_sqrt2, add(t1.x, t2.x)), mul(half_sqrt2, add(t1.y, t2.y)));
-          }
-          if (scale_out) e = make_double2(mul(e.x, p.out_scale), mul(e.y, p.out_scale));
-          __stcs(o + s * p.f_stride, e);
+      for (int s = 0; s < NSYM; s++) {
+        const int pp = DIM == 3 ? P3[s] : P2[s], qq = DIM == 3 ? Q3[s] : Q2[s];
+        double2 e;
+        if (pp == qq) {
+          // 0.5*(B_p u_p + u_p B_p): both products are bit-identical, so the sum is an
+          // exact doubling and the half undoes it exactly (:206, :223)
+          e = cmul(B[pp], u[j][pp]);
+        } else {
+          const double2 t1 = cmul(B[pp], u[j][qq]);
+          const double2 t2 = cmul(u[j][pp], B[qq]);
+          e = make_double2(mul(half_sqrt2, add(t1.x, t2.x)), mul(half_sqrt2, add(t1.y, t2.y)));
         }
+        if (scale_out) e = make_double2(mul(e.x, p.out_scale), mul(e.y, p.out_scale));
+        __stcs(o + s * p.f_stride, e);
       }
     }
   }
@@ -614,12 +679,14 @@ __global__ void __launch_bounds__(256, 2) strain_displacement_kernel(const Apply
 //   MODE 0: u^ = K^-1 f^                      (exact inverse of the stiffness apply, u^(0) = 0)
 //   MODE 1: u^ = K^-1 (tau^ . conj(B^))        (bri17.hpp:324-341)
 //   MODE 2: eta^ = sym(B^ (x) u^), u^ of MODE 1 (bri17.hpp:342-353): -strain induced by an eigenstress
+//   MODE 3: f^ = tau^ . conj(B^)              (bri17.hpp:340 without the solve: the modal force that
+//                                              is the right-hand side of the inclusion problem)
 // K^ and B^ are rebuilt per mode from the tables; the 2x2/3x3 Cholesky runs in registers.
 // Input/output element (s, i) at base[i*mstride + s*cstride]: planar (mstride 1) or
 // mode-major (cstride 1), the layout of python/demo.py:21,37-38.
 // ---------------------------------------------------------------------------
 struct AxisFactors {
-  double phi, chi, psi, c, s, alpha;
+  double phi, chi, psi, c, s, sa;
 };
 __device__ __forceinline__ AxisFactors axis_factors(const double *tab, int N, int k) {
   AxisFactors f;
@@ -628,7 +695,7 @@ __device__ __forceinline__ AxisFactors axis_factors(const double *tab, int N, in
   f.psi = __ldg(tab + size_t(TAB_PSI) * N + k);
   f.c = __ldg(tab + size_t(TAB_C) * N + k);
   f.s = __ldg(tab + size_t(TAB_S) * N + k);
-  f.alpha = __ldg(tab + size_t(TAB_ALPHA) * N + k);
+  f.sa = __ldg(tab + size_t(TAB_SINA) * N + k);
   return f;
 }
 
@@ -684,7 +751,7 @@ __global__ void __launch_bounds__(256, 2) modal_solve_kernel(const ApplyParams p
         phi[DIM - 1] = fI[j].phi; chi[DIM - 1] = fI[j].chi; psi[DIM - 1] = fI[j].psi;
         c[DIM - 1] = fI[j].c; sh[DIM - 1] = fI[j].s;
         double K[DIM][DIM];
-        stiffness_entries<DIM>(phi, chi, psi, p.mu, p.scaling, K);
+        if constexpr (MODE != 3) stiffness_entries<DIM>(phi, chi, psi, p.mu, p.scaling, K);
         Cplx u[DIM];
         if constexpr (MODE == 0) {
 #pragma unroll
@@ -693,15 +760,18 @@ __global__ void __launch_bounds__(256, 2) modal_solve_kernel(const ApplyParams p
 #pragma unroll
           for (int d = 0; d < DIM; d++) out[d] = u[d];
         } else {
-          double sum_alpha = f0.alpha;
-          if constexpr (DIM == 3) sum_alpha = sum_alpha + f1.alpha;
-          sum_alpha = sum_alpha + fI[j].alpha;
-          double sn, cs;
-          sincos(sum_alpha, &sn, &cs);
+          // e^{i sum(alpha)} from the per-axis (cos, sin) table entries (see modal_B)
+          double2 e = make_double2(f0.c, f0.sa);
+          if constexpr (DIM == 3) e = rot_mul(e, make_double2(f1.c, f1.sa));
+          e = rot_mul(e, make_double2(fI[j].c, fI[j].sa));
           Cplx B[DIM];
-          strain_displacement_entries<DIM>(c, sh, Cplx{-2. * sn, 2. * cs}, B);
-          eigenstress_to_displacement<DIM>(in, B, K, u);
-          if constexpr (MODE == 1) {
+          strain_displacement_entries<DIM>(c, sh, Cplx{-2. * e.y, 2. * e.x}, B);
+          if constexpr (MODE == 3) {
+            eigenstress_to_force<DIM>(in, B, u);
+          } else {
+            eigenstress_to_displacement<DIM>(in, B, K, u);
+          }
+          if constexpr (MODE == 1 || MODE == 3) {
 #pragma unroll
             for (int d = 0; d < DIM; d++) out[d] = u[d];
           } else {
@@ -807,6 +877,8 @@ static void fill_params(const bri17_plan *p, const Block &b, ApplyParams *ap) {
   ap->f = nullptr;
   ap->u_stride = ap->f_stride = 0;
   ap->u_mstride = ap->f_mstride = 1;
+  ap->dot_partial = nullptr;
+  ap->herm_n = 0;
 }
 
 static int check_launch(const char *what) {
@@ -824,10 +896,15 @@ static bool rows_fill_tiles(const Block &b, int tile) {
   return padded * 100 <= (long long)n_inner * 103;
 }
 
-static int launch_apply_flat(bri17_plan *p, const Block &b, ApplyParams &ap, cudaStream_t stream) {
+static int launch_apply_flat(bri17_plan *p, const Block &b, ApplyParams &ap, cudaStream_t stream,
+                             int max_grid = 0) {
   constexpr int THREADS = 256, VEC = 2;
-  void (*kern)(const ApplyParams) = b.dim == 3 ? modal_stiffness_apply_flat_kernel<3, THREADS, VEC, 2>
-                                                : modal_stiffness_apply_flat_kernel<2, THREADS, VEC, 2>;
+  const bool dot = ap.dot_partial != nullptr;
+  void (*kern)(const ApplyParams) =
+      dot ? (b.dim == 3 ? modal_stiffness_apply_flat_kernel<3, THREADS, VEC, 2, true>
+                        : modal_stiffness_apply_flat_kernel<2, THREADS, VEC, 2, true>)
+          : (b.dim == 3 ? modal_stiffness_apply_flat_kernel<3, THREADS, VEC, 2, false>
+                        : modal_stiffness_apply_flat_kernel<2, THREADS, VEC, 2, false>);
   const int n_mid = b.dim == 3 ? b.n[1] : 0;
   size_t smem = size_t(3) * (size_t(b.n[0]) + n_mid + b.n[b.dim - 1]) * sizeof(double);
   if (smem <= 48 * 1024) ap.stage_outer = 1; else { smem = 0; ap.stage_outer = 0; }
@@ -836,12 +913,38 @@ static int launch_apply_flat(bri17_plan *p, const Block &b, ApplyParams &ap, cud
   if (occ < 1) return fail(BRI17_ERR_CUDA, "flat apply kernel does not fit on an SM");
   make_geom(b, THREADS * VEC, p->sm_count * occ, &ap.g);
   const long long tiles = (b.modes + THREADS * VEC - 1) / (THREADS * VEC);
-  const int grid = int(std::min<long long>(tiles, (long long)p->sm_count * occ));
+  int grid = int(std::min<long long>(tiles, (long long)p->sm_count * occ));
+  if (max_grid > 0) grid = std::min(grid, max_grid);
   kern<<<grid, THREADS, smem, stream>>>(ap);
   p->last_grid = grid; p->last_block = THREADS; p->last_smem = int64_t(smem);
   p->last_flat = 1;
   p->launches++;
   return check_launch("modal_stiffness_apply_flat");
+}
+
+// Stiffness apply that also returns sum_k w_k Re(u^_k^H f^_k) in *dot_out (device scalar);
+// `scratch` receives one partial sum per CTA, so the grid is capped at scratch_count.
+int launch_apply_dot(bri17_plan *p, const Block &b, const void *u, void *f, int64_t u_stride,
+                     int64_t f_stride, double out_scale, int herm_n, double *dot_out, double *scratch,
+                     int scratch_count, cudaStream_t stream) {
+  if (b.modes == 0) {
+    BRI17_CUDA_TRY(cudaMemsetAsync(dot_out, 0, sizeof(double), stream));
+    return BRI17_OK;
+  }
+  ApplyParams ap;
+  fill_params(p, b, &ap);
+  ap.u = static_cast<const double2 *>(u);
+  ap.f = static_cast<double2 *>(f);
+  ap.u_stride = u_stride;
+  ap.f_stride = f_stride;
+  ap.out_scale = out_scale;
+  ap.dot_partial = scratch;
+  ap.herm_n = herm_n;
+  int rc = launch_apply_flat(p, b, ap, stream, scratch_count);
+  if (rc) return rc;
+  dot_finish_kernel<<<1, 256, 0, stream>>>(scratch, int(p->last_grid.load()), dot_out);
+  p->launches++;
+  return check_launch("dot_finish");
 }
 
 int launch_apply(bri17_plan *p, const Block &b, const void *u, void *f, int64_t u_stride,
@@ -907,9 +1010,9 @@ int launch_stiffness_field(bri17_plan *p, const Block &b, void *K, cudaStream_t 
   ApplyParams ap;
   fill_params(p, b, &ap);
   ap.f = static_cast<double2 *>(K);
-  const int grid = make_geom(b, 512, p->sm_count * 4, &ap.g);
-  if (b.dim == 3) modal_stiffness_field_kernel<3><<<grid, 256, 0, stream>>>(ap);
-  else modal_stiffness_field_kernel<2><<<grid, 256, 0, stream>>>(ap);
+  const int grid = make_geom(b, 256, p->sm_count * 4, &ap.g);
+  if (b.dim == 3) modal_field_kernel<3, 1><<<grid, 256, 0, stream>>>(ap);
+  else modal_field_kernel<2, 1><<<grid, 256, 0, stream>>>(ap);
   p->launches++;
   return check_launch("modal_stiffness_field");
 }
@@ -918,9 +1021,9 @@ int launch_strain_field(bri17_plan *p, const Block &b, void *B, cudaStream_t str
   ApplyParams ap;
   fill_params(p, b, &ap);
   ap.f = static_cast<double2 *>(B);
-  const int grid = make_geom(b, 512, p->sm_count * 2, &ap.g);
-  if (b.dim == 3) strain_displacement_kernel<3, 0><<<grid, 256, 0, stream>>>(ap);
-  else strain_displacement_kernel<2, 0><<<grid, 256, 0, stream>>>(ap);
+  const int grid = make_geom(b, 256, p->sm_count * 8, &ap.g);
+  if (b.dim == 3) modal_field_kernel<3, 0><<<grid, 256, 0, stream>>>(ap);
+  else modal_field_kernel<2, 0><<<grid, 256, 0, stream>>>(ap);
   p->launches++;
   return check_launch("modal_strain_displacement_field");
 }
@@ -936,8 +1039,8 @@ int launch_strain_apply(bri17_plan *p, const Block &b, const void *u, void *eps,
   ap.f_stride = e_stride;
   ap.out_scale = out_scale;
   const int grid = make_geom(b, 512, p->sm_count * 2, &ap.g);
-  if (b.dim == 3) strain_displacement_kernel<3, 1><<<grid, 256, 0, stream>>>(ap);
-  else strain_displacement_kernel<2, 1><<<grid, 256, 0, stream>>>(ap);
+  if (b.dim == 3) strain_displacement_kernel<3><<<grid, 256, 0, stream>>>(ap);
+  else strain_displacement_kernel<2><<<grid, 256, 0, stream>>>(ap);
   p->launches++;
   return check_launch("strain_displacement_apply");
 }
@@ -951,16 +1054,18 @@ int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, 
   ap.u_stride = in_cs; ap.u_mstride = in_ms;
   ap.f_stride = out_cs; ap.f_mstride = out_ms;
   // two modes per thread for the lighter maps (more loads in flight), one for eigenstress -> strain
-  const int vec = (mode == 0 || (mode == 1 && b.dim == 2)) ? 2 : 1;   // register budget: no spills at 128
+  const int vec = (mode == 0 || mode == 3 || (mode == 1 && b.dim == 2)) ? 2 : 1;   // register budget: no spills at 128
   const int grid = make_geom(b, 256 * vec, p->sm_count * 2, &ap.g);
   if (b.dim == 3) {
     if (mode == 0) modal_solve_kernel<3, 0, 2><<<grid, 256, 0, stream>>>(ap);
     else if (mode == 1) modal_solve_kernel<3, 1, 1><<<grid, 256, 0, stream>>>(ap);
-    else modal_solve_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 2) modal_solve_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(ap);
+    else modal_solve_kernel<3, 3, 2><<<grid, 256, 0, stream>>>(ap);
   } else {
     if (mode == 0) modal_solve_kernel<2, 0, 2><<<grid, 256, 0, stream>>>(ap);
     else if (mode == 1) modal_solve_kernel<2, 1, 2><<<grid, 256, 0, stream>>>(ap);
-    else modal_solve_kernel<2, 2, 1><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 2) modal_solve_kernel<2, 2, 1><<<grid, 256, 0, stream>>>(ap);
+    else modal_solve_kernel<2, 3, 2><<<grid, 256, 0, stream>>>(ap);
   }
   p->launches++;
   return check_launch("modal_solve");

@@ -64,55 +64,91 @@ BRI17_HD void strain_displacement_entries(const double *c, const double *s, Cplx
 
 // x <- K^-1 x for a real SPD K (destroyed), complex x: Cholesky K = L L^T,
 // forward then backward substitution.  Stands in for Eigen's K.llt().solve(rhs)
-// (bri17.hpp:341), whose exact operation order no reference test pins.
+// (bri17.hpp:341) in the operation order Eigen 3.3/3.4 uses for fixed sizes:
+// llt_inplace<Lower>::unblocked (x = A_kk - A10.squaredNorm(); A21 -= A20 * A10^H;
+// A21 /= x) and the unrolled triangular solves (rhs_i -= (row_i . rhs).sum();
+// rhs_i /= L_ii): sums of products are formed first and subtracted once.  No
+// reference test pins the result (parity unpinned).
 template <int DIM>
 BRI17_HD void cholesky_solve(double (&A)[DIM][DIM], Cplx (&x)[DIM]) {
 #ifdef __CUDA_ARCH__
   // Device: fp64 divide and sqrt are ~30-instruction software sequences and would make
-  // the batched solve FP64-bound.  Same factorisation with one rsqrt per pivot and
-  // multiplications by the reciprocal pivots (differs from the host path by a few ulp;
-  // this method is parity-unpinned and tested at 1e-12).
+  // the batched solve FP64-bound.  Same factorisation and grouping with one rsqrt per
+  // pivot and multiplications by the reciprocal pivots (differs from the host path by a
+  // few ulp; tested at 1e-12).
   double r[DIM];  // 1 / L_jj
   for (int j = 0; j < DIM; j++) {
     double d = A[j][j];
-    for (int p = 0; p < j; p++) d -= A[j][p] * A[j][p];
+    if (j > 0) {
+      double sq = A[j][0] * A[j][0];
+      for (int p = 1; p < j; p++) sq = sq + A[j][p] * A[j][p];
+      d = d - sq;
+    }
     r[j] = rsqrt(d);
     for (int i = j + 1; i < DIM; i++) {
       double t = A[i][j];
-      for (int p = 0; p < j; p++) t -= A[i][p] * A[j][p];
+      if (j > 0) {
+        double dot = A[i][0] * A[j][0];
+        for (int p = 1; p < j; p++) dot = dot + A[i][p] * A[j][p];
+        t = t - dot;
+      }
       A[i][j] = t * r[j];
     }
   }
   for (int i = 0; i < DIM; i++) {
     Cplx t = x[i];
-    for (int p = 0; p < i; p++) t = csub(t, cscale(A[i][p], x[p]));
+    if (i > 0) {
+      Cplx acc = cscale(A[i][0], x[0]);
+      for (int p = 1; p < i; p++) acc = cadd(acc, cscale(A[i][p], x[p]));
+      t = csub(t, acc);
+    }
     x[i] = cscale(r[i], t);
   }
   for (int i = DIM - 1; i >= 0; i--) {
     Cplx t = x[i];
-    for (int p = i + 1; p < DIM; p++) t = csub(t, cscale(A[p][i], x[p]));
+    if (i < DIM - 1) {
+      Cplx acc = cscale(A[i + 1][i], x[i + 1]);
+      for (int p = i + 2; p < DIM; p++) acc = cadd(acc, cscale(A[p][i], x[p]));
+      t = csub(t, acc);
+    }
     x[i] = cscale(r[i], t);
   }
 #else
   for (int j = 0; j < DIM; j++) {
     double d = A[j][j];
-    for (int p = 0; p < j; p++) d -= A[j][p] * A[j][p];
+    if (j > 0) {
+      double sq = A[j][0] * A[j][0];
+      for (int p = 1; p < j; p++) sq = sq + A[j][p] * A[j][p];
+      d = d - sq;
+    }
     d = sqrt(d);
     A[j][j] = d;
     for (int i = j + 1; i < DIM; i++) {
       double t = A[i][j];
-      for (int p = 0; p < j; p++) t -= A[i][p] * A[j][p];
+      if (j > 0) {
+        double dot = A[i][0] * A[j][0];
+        for (int p = 1; p < j; p++) dot = dot + A[i][p] * A[j][p];
+        t = t - dot;
+      }
       A[i][j] = t / d;
     }
   }
   for (int i = 0; i < DIM; i++) {
     Cplx t = x[i];
-    for (int p = 0; p < i; p++) t = csub(t, cscale(A[i][p], x[p]));
+    if (i > 0) {
+      Cplx acc = cscale(A[i][0], x[0]);
+      for (int p = 1; p < i; p++) acc = cadd(acc, cscale(A[i][p], x[p]));
+      t = csub(t, acc);
+    }
     x[i] = cdivr(t, A[i][i]);
   }
   for (int i = DIM - 1; i >= 0; i--) {
     Cplx t = x[i];
-    for (int p = i + 1; p < DIM; p++) t = csub(t, cscale(A[p][i], x[p]));
+    if (i < DIM - 1) {
+      Cplx acc = cscale(A[i + 1][i], x[i + 1]);
+      for (int p = i + 2; p < DIM; p++) acc = cadd(acc, cscale(A[p][i], x[p]));
+      t = csub(t, acc);
+    }
     x[i] = cdivr(t, A[i][i]);
   }
 #endif
@@ -136,10 +172,10 @@ BRI17_HD void mandel_pair(int s, int &p, int &q) {
   }
 }
 
-// u = K^-1 (tau . conj(B))  (bri17.hpp:324-341).  tau in Mandel notation.  K is destroyed.
+// f = tau . conj(B)  (bri17.hpp:324-332, :340): the right-hand side of the per-mode solve,
+// i.e. the modal force equivalent to the eigenstress tau (Mandel notation).
 template <int DIM>
-BRI17_HD void eigenstress_to_displacement(const Cplx *tau, const Cplx (&B)[DIM], double (&K)[DIM][DIM],
-                                          Cplx (&u)[DIM]) {
+BRI17_HD void eigenstress_to_force(const Cplx *tau, const Cplx (&B)[DIM], Cplx (&f)[DIM]) {
   Cplx t[DIM][DIM];
   for (int s = 0; s < Mandel<DIM>::nsym; s++) {
     int p, q;
@@ -156,8 +192,15 @@ BRI17_HD void eigenstress_to_displacement(const Cplx *tau, const Cplx (&B)[DIM],
   for (int i = 0; i < DIM; i++) {
     Cplx acc = cmulc(t[i][0], cconj(B[0]));
     for (int j = 1; j < DIM; j++) acc = cadd(acc, cmulc(t[i][j], cconj(B[j])));
-    u[i] = acc;
+    f[i] = acc;
   }
+}
+
+// u = K^-1 (tau . conj(B))  (bri17.hpp:324-341).  tau in Mandel notation.  K is destroyed.
+template <int DIM>
+BRI17_HD void eigenstress_to_displacement(const Cplx *tau, const Cplx (&B)[DIM], double (&K)[DIM][DIM],
+                                          Cplx (&u)[DIM]) {
+  eigenstress_to_force<DIM>(tau, B, u);
   cholesky_solve<DIM>(K, u);
 }
 

@@ -34,6 +34,7 @@ static void fill_axis_tables(AxisTables &t, int n, double L) {
   double *c = t.host.data() + size_t(TAB_C) * n;
   double *s = t.host.data() + size_t(TAB_S) * n;
   double *al = t.host.data() + size_t(TAB_ALPHA) * n;
+  double *sa = t.host.data() + size_t(TAB_SINA) * n;
   for (int k = 0; k < n; k++) {
     const double h = L / n;                                   // :259
     const double beta = 2 * std::numbers::pi_v<double> * k / n;  // :260
@@ -43,7 +44,8 @@ static void fill_axis_tables(AxisTables &t, int n, double L) {
     const double alpha = std::numbers::pi_v<double> * k / n;  // :218
     c[k] = std::cos(alpha);                                   // :220
     s[k] = std::sin(alpha) * n / L;                           // :221
-    al[k] = alpha;                                            // summed per mode on the device (:219)
+    al[k] = alpha;                                            // summed per mode by the host path (:219)
+    sa[k] = std::sin(alpha);                                  // device: e^{i sum(alpha)} = prod (c + i sa), :224
   }
 }
 
@@ -172,6 +174,7 @@ int bri17_plan_destroy(bri17_plan *p) {
 
 int bri17_plan_set_option(bri17_plan *p, const char *key, int64_t value) {
   if (!p || !key) return fail(BRI17_ERR_INVALID_ARG, "plan/key is NULL");
+  std::lock_guard<std::mutex> lock(p->host_mutex);  // the host_* options free the staging set
   if (!std::strcmp(key, "apply_variant")) {
     if (value < -1 || value >= num_variants())
       return fail(BRI17_ERR_INVALID_ARG, "apply_variant out of range");
@@ -201,11 +204,11 @@ int bri17_plan_get_info(const bri17_plan *p, const char *key, int64_t *value) {
   if (!std::strcmp(key, "num_variants")) *value = num_variants();
   else if (!std::strcmp(key, "apply_variant")) *value = p->apply_variant < 0 ? default_variant(p) : p->apply_variant;
   else if (!std::strcmp(key, "sm_count")) *value = p->sm_count;
-  else if (!std::strcmp(key, "last_grid")) *value = p->last_grid;
-  else if (!std::strcmp(key, "last_block")) *value = p->last_block;
-  else if (!std::strcmp(key, "last_smem")) *value = p->last_smem;
-  else if (!std::strcmp(key, "launches")) *value = p->launches;
-  else if (!std::strcmp(key, "last_flat")) *value = p->last_flat;
+  else if (!std::strcmp(key, "last_grid")) *value = p->last_grid.load();
+  else if (!std::strcmp(key, "last_block")) *value = p->last_block.load();
+  else if (!std::strcmp(key, "last_smem")) *value = p->last_smem.load();
+  else if (!std::strcmp(key, "launches")) *value = p->launches.load();
+  else if (!std::strcmp(key, "last_flat")) *value = p->last_flat.load();
   else if (!std::strcmp(key, "device")) *value = p->device;
   else if (!std::strcmp(key, "table_bytes")) {
     int64_t b = 0;
@@ -372,6 +375,33 @@ int bri17_eigenstress_to_opposite_strain_f64(bri17_plan *p, const void *tau, voi
   return solve_entry(p, 2, tau, eta, k_begin, local_shape, comp_stride, mode_stride, comp_stride, mode_stride, stream);
 }
 
+int bri17_eigenstress_to_force_f64(bri17_plan *p, const void *tau, void *f, const int *k_begin,
+                                   const int *local_shape, int64_t tau_cs, int64_t tau_ms,
+                                   int64_t f_cs, int64_t f_ms, void *stream) {
+  return solve_entry(p, 3, tau, f, k_begin, local_shape, tau_cs, tau_ms, f_cs, f_ms, stream);
+}
+
+int bri17_modal_stiffness_apply_dot_f64(bri17_plan *p, const void *u, void *f, const int *k_begin,
+                                        const int *local_shape, int64_t comp_stride, double out_scale,
+                                        int hermitian_n, double *dot_dev, double *scratch_dev,
+                                        int scratch_count, void *stream) {
+  if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");
+  if (!dot_dev || !scratch_dev || scratch_count < 1)
+    return fail(BRI17_ERR_INVALID_ARG, "dot_dev/scratch_dev is NULL or scratch_count < 1");
+  if (hermitian_n < 0) return fail(BRI17_ERR_INVALID_ARG, "hermitian_n < 0");
+  Block b;
+  int rc = make_block(p, k_begin, local_shape, &b);
+  if (rc) return rc;
+  if (b.modes > 0 && ((rc = check_dev_ptr(u, "u_hat_dev")) || (rc = check_dev_ptr(f, "f_hat_dev")))) return rc;
+  if (comp_stride == 0) comp_stride = b.modes;
+  if (comp_stride < b.modes)
+    return fail(BRI17_ERR_INVALID_ARG, "comp_stride smaller than the block");
+  return on_device(p, [&] {
+    return launch_apply_dot(p, b, u, f, comp_stride, comp_stride, out_scale, hermitian_n, dot_dev,
+                            scratch_dev, scratch_count, cudaStream_t(stream));
+  });
+}
+
 int bri17_modal_stiffness_apply_f64(bri17_plan *p, const void *u, void *f, const int *k_begin,
                                     const int *local_shape, int64_t comp_stride,
                                     double out_scale, void *stream) {
@@ -401,6 +431,8 @@ int bri17_modal_stiffness_apply_host_f64(bri17_plan *p, const void *u, void *f,
   if (comp_stride == 0) comp_stride = b.modes;
   if (comp_stride < b.modes)
     return fail(BRI17_ERR_INVALID_ARG, "comp_stride smaller than the block");
+  // one staging set per plan: concurrent host-buffer calls on the same plan take turns
+  std::lock_guard<std::mutex> lock(p->host_mutex);
   return on_device(p, [&] { return apply_host(p, b, u, f, comp_stride, out_scale); });
 }
 

@@ -13,18 +13,35 @@
 //           unpack on the way back (2 extra HBM passes per apply);
 //   mode 1: the same kernel stores straight into the peers' buffers through
 //           CUDA-IPC mappings (NVLink peer memory): the transposition IS the
-//           transfer, no pack/unpack pass, NCCL only as a stream-ordered barrier.
+//           transfer, no pack/unpack pass.  Cross-GPU synchronisation = release/
+//           acquire flags in the same peer-mapped memory (flag_barrier_kernel, a few
+//           microseconds; round 1 used a 1-element ncclAllReduce, ~20 us each), and
+//           the CG scalars are summed the same way (peer_allreduce_kernel).  NCCL is
+//           only used at plan creation (IPC handle all-gather) in this mode.
+//
+// Axis 0: when N0 is a supported power of two the three passes  FFT(axis 0) -> K^ ->
+// inverse FFT(axis 0)  are ONE kernel (axis0_fused.cuh); otherwise cuFFT + the modal kernel.
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "axis0_fused.cuh"
 #include "bri17_b200_realspace.h"
 #include "internal.h"
+
+namespace bri17b200 {
+namespace axis0 {
+int launch(Params p, int dim, int sm_count, int max_grid, cudaStream_t st, int *grid_out);
+void fill_twiddles(int N0, double2 *tw);
+int emulate(const Params &p, int dim, double *dot_out);
+}  // namespace axis0
+}  // namespace bri17b200
 
 // libbri17_b200.so keeps its internals hidden: this library has its own copy of the
 // error helpers, which forward to the exported thread-local message of the core library.
@@ -129,9 +146,92 @@ __global__ void scale_kernel(double2 *x, long long n, double scale) {
   }
 }
 
+// ---- cross-GPU flags in peer memory (exchange mode 1) -------------------------------------
+// Every rank owns one page of 64-bit words at the tail of its exchange buffer W, mapped by all
+// peers through the same CUDA-IPC handle as W itself:
+//   [FLAG_BAR0 + q]  barrier counter written by rank q, caller's stream
+//   [FLAG_BAR1 + q]  same for the exchange stream of the pipelined apply
+//   [FLAG_RED + q]   all-reduce counter written by rank q
+//   [FLAG_VAL + (parity*MAX_RANKS + q)*RED_MAX + i]   all-reduce values of rank q (doubles)
+// Counters only grow; every rank executes the same sequence of barriers / reductions per stream,
+// so "counter >= my epoch" is the arrival test.
+constexpr int FLAG_BAR0 = 0, FLAG_BAR1 = 16, FLAG_RED = 32, FLAG_VAL = 64, RED_MAX = 8;
+constexpr int FLAG_WORDS = FLAG_VAL + 2 * MAX_RANKS * RED_MAX;  // 320 words
+constexpr size_t FLAG_BYTES = 4096;
+static_assert(FLAG_WORDS * 8 <= FLAG_BYTES, "flag page too small");
+constexpr unsigned long long SPIN_TIMEOUT_NS = 60ull * 1000000000ull;
+
+struct PeerFlags {
+  unsigned long long *page[MAX_RANKS];  // flag page of every rank (own page at [rank])
+  int rank, nranks;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Spins until *p >= epoch.  A peer that never arrives (crashed rank) must not hang the GPU:
+// after SPIN_TIMEOUT_NS the kernel traps, which surfaces as a CUDA error on the host.
+__device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned long long epoch) {
+  const unsigned long long t0 = global_timer_ns();
+  while (ld_acquire_sys(p) < epoch) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) __trap();
+  }
+}
+
+// Stream-ordered barrier across the ranks: lane q tells rank q "I am at `epoch`" and waits for
+// rank q's message.  Everything this GPU wrote before (earlier kernels of the stream, including
+// stores into peer memory) is released to the system first; everything peers wrote before their
+// arrival is acquired.
+__global__ void flag_barrier_kernel(PeerFlags f, int base, unsigned long long epoch) {
+  const int q = threadIdx.x;
+  if (q >= f.nranks || q == f.rank) return;
+  __threadfence_system();
+  st_release_sys(f.page[q] + base + f.rank, epoch);
+  wait_flag(f.page[f.rank] + base + q, epoch);
+  __threadfence_system();
+}
+
+// v[0..n) <- sum over ranks of v[0..n), n <= RED_MAX, in rank order on every rank (deterministic
+// and identical everywhere).  One warp: lane q pushes this rank's values into rank q's page.
+__global__ void peer_allreduce_kernel(PeerFlags f, double *v, int n, unsigned long long epoch) {
+  const int q = threadIdx.x;
+  const int par = int(epoch & 1);
+  if (q < f.nranks) {
+    double *dst = reinterpret_cast<double *>(f.page[q] + FLAG_VAL) + (par * MAX_RANKS + f.rank) * RED_MAX;
+    for (int i = 0; i < n; i++) dst[i] = v[i];
+    if (q != f.rank) {
+      st_release_sys(f.page[q] + FLAG_RED + f.rank, epoch);
+      wait_flag(f.page[f.rank] + FLAG_RED + q, epoch);
+    }
+  }
+  __syncwarp();
+  if (q < n) {
+    const double *src = reinterpret_cast<const double *>(f.page[f.rank] + FLAG_VAL) + par * MAX_RANKS * RED_MAX;
+    double acc = 0.;
+    for (int r = 0; r < f.nranks; r++) acc += reinterpret_cast<const volatile double *>(src)[r * RED_MAX + q];
+    v[q] = acc;
+  }
+}
+
 // ---- CG vector kernels (K5): deterministic two-stage reductions, device scalars ----
 // Vectors are plain double arrays (a complex field is its interleaved doubles:
 // sum x.y over doubles = sum Re(x conj y)), processed as double2 when possible.
+// Per iteration (cg_core): the operator application returns <p, A p> itself (Parseval sum in
+// the modal kernel), then
+//   cg_residual_kernel:  r -= alpha A p, partial <r, r>          (2 reads + 1 write)
+//   cg_direction_kernel: x += alpha p,  p = r + beta p           (3 reads + 2 writes)
+// = 8 vector passes; round 1 spent 11 (separate <p, A p> pass, x updated with r).
 constexpr int RED_CTAS = 1184;  // 148 SMs x 8
 constexpr int RED_THREADS = 256;
 
@@ -148,22 +248,6 @@ __device__ __forceinline__ double block_sum(double v) {
   return t;  // valid in thread 0
 }
 
-// partial[b] = sum over this CTA's elements of x*y      (n2 = number of double2 pairs, tail = odd element)
-__global__ void __launch_bounds__(RED_THREADS) cg_dot_kernel(const double *x, const double *y, long long n,
-                                                              double *partial) {
-  const double2 *x2 = reinterpret_cast<const double2 *>(x), *y2 = reinterpret_cast<const double2 *>(y);
-  const long long n2 = n >> 1;
-  double acc = 0.;
-  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n2;
-       i += (long long)gridDim.x * RED_THREADS) {
-    const double2 a = x2[i], b = y2[i];
-    acc += a.x * b.x + a.y * b.y;
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc += x[n - 1] * y[n - 1];
-  acc = block_sum(acc);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
-}
-
 __global__ void __launch_bounds__(RED_THREADS) cg_finish_kernel(const double *partial, int n, double *out) {
   double acc = 0.;
   for (int i = threadIdx.x; i < n; i += RED_THREADS) acc += partial[i];
@@ -171,26 +255,70 @@ __global__ void __launch_bounds__(RED_THREADS) cg_finish_kernel(const double *pa
   if (threadIdx.x == 0) *out = acc;
 }
 
-// alpha = rr/pAp;  x += alpha p;  r -= alpha Ap;  partial <r,r>   (fused axpy + axpy + dot)
-__global__ void __launch_bounds__(RED_THREADS) cg_update_kernel(double *x, double *r, const double *p,
-                                                                 const double *Ap, long long n, const double *rr,
-                                                                 const double *pAp, double *partial) {
-  const double alpha = *rr / *pAp;
-  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
-  const double2 *p2 = reinterpret_cast<const double2 *>(p), *A2 = reinterpret_cast<const double2 *>(Ap);
+// Sums of the `nslot` interleaved sub-fields of b: slot = c*inter + t for value (c*count + i)*inter + t
+// (complex fields: inter = 2, real and imaginary parts are separate slots).  grid = (CTAs, nslot).
+constexpr int MEAN_CTAS = 148;
+__global__ void __launch_bounds__(RED_THREADS) cg_slot_sum_kernel(const double *b, long long count, int inter,
+                                                                   double *partial) {
+  const int slot = blockIdx.y, c = slot / inter, t = slot % inter;
+  const double *src = b + (long long)c * count * inter + t;
+  double acc = 0.;
+  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < count;
+       i += (long long)gridDim.x * RED_THREADS)
+    acc += src[i * inter];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partial[slot * MEAN_CTAS + blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(RED_THREADS) cg_slot_finish_kernel(const double *partial, double *sums) {
+  double acc = 0.;
+  for (int i = threadIdx.x; i < MEAN_CTAS; i += RED_THREADS) acc += partial[blockIdx.x * MEAN_CTAS + i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) sums[blockIdx.x] = acc;
+}
+
+// r = p = b - mean(slot), x = 0, partial <r, r>: the zero-frequency component of the right-hand
+// side is projected out (K^(0) = 0: bri17.hpp:336-339 skips the null frequency, theory.rst:208-212).
+__global__ void __launch_bounds__(RED_THREADS) cg_init_kernel(const double *b, double *x, double *r, double *p,
+                                                               long long count, int inter, int nslot,
+                                                               const double *sums, double inv_total,
+                                                               double *partial) {
+  const long long n = count * inter * (nslot / inter);
+  double acc = 0.;
+  for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n;
+       i += (long long)gridDim.x * RED_THREADS) {
+    const int slot = int(i / (count * inter)) * inter + int(i % inter);
+    const double v = b[i] - sums[slot] * inv_total;
+    x[i] = 0.;
+    r[i] = v;
+    p[i] = v;
+    acc += v * v;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// Breakdown guards: a zero denominator (r == 0 exactly, or a null direction) freezes the
+// iteration instead of producing NaN; the host stops at its next residual check.
+__device__ __forceinline__ double safe_ratio(double num, double den) { return den > 0. ? num / den : 0.; }
+
+// alpha = rr/pAp;  r -= alpha Ap;  partial <r,r>
+__global__ void __launch_bounds__(RED_THREADS) cg_residual_kernel(double *r, const double *Ap, long long n,
+                                                                   const double *rr, const double *pAp,
+                                                                   double *partial) {
+  const double alpha = safe_ratio(*rr, *pAp);
+  double2 *r2 = reinterpret_cast<double2 *>(r);
+  const double2 *A2 = reinterpret_cast<const double2 *>(Ap);
   const long long n2 = n >> 1;
   double acc = 0.;
   for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n2;
        i += (long long)gridDim.x * RED_THREADS) {
-    const double2 pi = p2[i], ai = A2[i];
-    double2 xi = x2[i], ri = r2[i];
-    xi.x += alpha * pi.x; xi.y += alpha * pi.y;
+    const double2 ai = A2[i];
+    double2 ri = r2[i];
     ri.x -= alpha * ai.x; ri.y -= alpha * ai.y;
-    x2[i] = xi; r2[i] = ri;
+    r2[i] = ri;
     acc += ri.x * ri.x + ri.y * ri.y;
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    x[n - 1] += alpha * p[n - 1];
     const double t = r[n - 1] - alpha * Ap[n - 1];
     r[n - 1] = t;
     acc += t * t;
@@ -199,21 +327,27 @@ __global__ void __launch_bounds__(RED_THREADS) cg_update_kernel(double *x, doubl
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
-// beta = rr_new/rr;  p = r + beta p
-__global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double *p, const double *r, long long n,
-                                                                    const double *rr_new, const double *rr) {
-  const double beta = *rr_new / *rr;
-  double2 *p2 = reinterpret_cast<double2 *>(p);
+// alpha = rr/pAp, beta = rr_new/rr;  x += alpha p;  p = r + beta p
+__global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double *x, double *p, const double *r,
+                                                                    long long n, const double *rr,
+                                                                    const double *pAp, const double *rr_new) {
+  const double alpha = safe_ratio(*rr, *pAp), beta = safe_ratio(*rr_new, *rr);
+  double2 *x2 = reinterpret_cast<double2 *>(x), *p2 = reinterpret_cast<double2 *>(p);
   const double2 *r2 = reinterpret_cast<const double2 *>(r);
   const long long n2 = n >> 1;
   for (long long i = blockIdx.x * (long long)RED_THREADS + threadIdx.x; i < n2;
        i += (long long)gridDim.x * RED_THREADS) {
     const double2 ri = r2[i];
-    double2 pi = p2[i];
+    double2 pi = p2[i], xi = x2[i];
+    xi.x += alpha * pi.x; xi.y += alpha * pi.y;
     pi.x = ri.x + beta * pi.x; pi.y = ri.y + beta * pi.y;
+    x2[i] = xi;
     p2[i] = pi;
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = r[n - 1] + beta * p[n - 1];
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    x[n - 1] += alpha * p[n - 1];
+    p[n - 1] = r[n - 1] + beta * p[n - 1];
+  }
 }
 
 }  // namespace
@@ -236,7 +370,8 @@ struct Layout {
 struct bri17_rs_plan {
   int dim = 0, shape[3] = {1, 1, 1};
   double L[3] = {1, 1, 1};
-  int device = 0, rank = 0, nranks = 1, mode = 0;
+  double mu = 0, nu = 0;
+  int device = 0, rank = 0, nranks = 1, mode = 0, sm_count = 148;
   int N2e = 1;                 // trailing extent in real space (N2 in 3-D, 1 in 2-D)
   int n0_beg[16 + 1];
   int n0_loc = 0;
@@ -244,7 +379,7 @@ struct bri17_rs_plan {
   double correction = 1.0;     // |h|/|N|, tests/test_bri17.cpp:93-98
   Layout lc, lr;               // complex (c2c) and real (r2c) layouts
   bri17_plan *modal = nullptr;
-  ncclComm_t comm = nullptr, comm_x = nullptr;   // comm_x: barriers on the exchange stream
+  ncclComm_t comm = nullptr;
   cudaStream_t sx = nullptr;                      // exchange stream of the pipelined apply
   cudaEvent_t ev_a[3] = {}, ev_b[3] = {};         // per-component hand-offs st <-> sx
   int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
@@ -254,6 +389,16 @@ struct bri17_rs_plan {
   int64_t real_upper = 0;      // element offset of the upper region of W2 used by the real path
   double2 *peerW[16] = {}, *peerW2[16] = {};
   double *barrier_word = nullptr;
+  // release/acquire flags in peer memory (mode 1): one page at the tail of every rank's W
+  PeerFlags flags{};
+  unsigned long long epoch_bar[2] = {0, 0}, epoch_red = 0;
+  // fused axis-0 pass (axis0_fused.cuh): own device copies of phi|chi|psi per axis + twiddles
+  int fused = 1;               // option "fused_axis0"; used when axis0::supported(shape[0])
+  double *tabs = nullptr;      // [axis][3][N_axis]
+  int64_t tab_off[3] = {0, 0, 0};
+  double2 *twiddle = nullptr;
+  double *dot_scratch = nullptr;  // one partial per CTA of the pass that also returns <u^, f^>
+  int64_t fused_launches = 0;
   cudaEvent_t ev[8 + 1] = {};
   bool timings_valid = false;
   // CG work space (doubles)
@@ -286,15 +431,32 @@ int choose_parts(int len, long long rows_total) {
   return parts;
 }
 
-// cross-GPU, stream-ordered barrier (and memory fence) = 1-element all-reduce
-int stream_barrier(bri17_rs_plan *p, cudaStream_t st) {
+// cross-GPU, stream-ordered barrier (and memory fence).  Mode 1: flags in peer memory
+// (which = 0 caller's stream, 1 exchange stream: independent counters); mode 0: 1-element all-reduce.
+int stream_barrier(bri17_rs_plan *p, cudaStream_t st, int which = 0) {
   if (p->nranks == 1) return BRI17_OK;
+  if (p->mode == 1) {
+    flag_barrier_kernel<<<1, 32, 0, st>>>(p->flags, which ? FLAG_BAR1 : FLAG_BAR0, ++p->epoch_bar[which]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BRI17_ERR_CUDA, std::string("flag barrier launch: ") + cudaGetErrorString(e));
+    return BRI17_OK;
+  }
   RS_NCCL_TRY(ncclAllReduce(p->barrier_word, p->barrier_word, 1, ncclDouble, ncclSum, p->comm, st));
   return BRI17_OK;
 }
-// same on the exchange stream of the pipelined apply, with its own communicator
-int exchange_barrier(bri17_rs_plan *p) {
-  RS_NCCL_TRY(ncclAllReduce(p->barrier_word + 8, p->barrier_word + 8, 1, ncclDouble, ncclSum, p->comm_x, p->sx));
+// same on the exchange stream of the pipelined apply (mode 1 only)
+int exchange_barrier(bri17_rs_plan *p) { return stream_barrier(p, p->sx, 1); }
+
+// v[0..n) <- sum over ranks, on the stream, result identical on every rank (n <= RED_MAX)
+int scalar_allreduce(bri17_rs_plan *p, double *v, int n, cudaStream_t st) {
+  if (p->nranks == 1) return BRI17_OK;
+  if (p->mode == 1) {
+    peer_allreduce_kernel<<<1, 32, 0, st>>>(p->flags, v, n, ++p->epoch_red);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BRI17_ERR_CUDA, std::string("peer all-reduce launch: ") + cudaGetErrorString(e));
+    return BRI17_OK;
+  }
+  RS_NCCL_TRY(ncclAllReduce(v, v, size_t(n), ncclDouble, ncclSum, p->comm, st));
   return BRI17_OK;
 }
 
@@ -537,18 +699,77 @@ int ensure_buffers(bri17_rs_plan *p, size_t bytes) {
   return BRI17_OK;
 }
 
-// The modal operator on the Fourier-side block of a layout, in place, scaled by |h|/|N|.
-int modal_on_block(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st) {
-  if (l.fourier_count == 0) return BRI17_OK;
+// Is the fused axis-0 pass used for this plan?
+bool use_fused(const bri17_rs_plan *p) { return p->fused && p->tabs && bri17b200::axis0::supported(p->shape[0]); }
+
+// Axis-0 section of the apply on the Fourier-side block X of a layout, in place:
+//   FFT(axis 0) -> K^ . (.) * |h|/|N| -> unnormalised inverse FFT(axis 0)
+// (tests/test_bri17.cpp:57 [axis 0], :58-92, :93-106, :95 [axis 0]).  One kernel when N0 is a
+// supported power of two, cuFFT + modal kernel + cuFFT otherwise.  dot_dev (optional, device
+// scalar) receives sum_k w_k Re(u^_k^H f^_k) over THIS rank's block (= its share of <u, A u>).
+// Events 3 and 4 bracket the modal kernel (or the whole fused pass).
+int modal_section(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st, double *dot_dev) {
+  const int dim = p->dim;
+  const int herm_n = l.real ? p->shape[dim - 1] : 0;
+  if (dot_dev && !p->dot_scratch) BRI17_CUDA_TRY(cudaMalloc(&p->dot_scratch, sizeof(double) * RED_CTAS));
+  if (l.fourier_count == 0) {
+    mark(p, 3, st);
+    mark(p, 4, st);
+    mark(p, 5, st);
+    if (dot_dev) BRI17_CUDA_TRY(cudaMemsetAsync(dot_dev, 0, sizeof(double), st));
+    return BRI17_OK;
+  }
+  if (use_fused(p)) {
+    mark(p, 3, st);
+    bri17b200::axis0::Params a{};
+    a.X = X;
+    a.comp_stride = l.fourier_count;
+    a.S = (long long)l.n1_loc * l.S2e;
+    a.N0 = p->shape[0];
+    a.S2e = dim == 3 ? l.S2e : 1;
+    a.k1_begin = l.k1_beg[p->rank];
+    a.tab0 = p->tabs + p->tab_off[0];
+    a.tab1 = p->tabs + p->tab_off[1];
+    a.tab2 = dim == 3 ? p->tabs + p->tab_off[2] : nullptr;
+    a.N1 = p->shape[1];
+    a.N2 = dim == 3 ? p->shape[2] : 1;
+    a.twiddle = p->twiddle;
+    a.mu = p->mu;
+    a.scaling = p->mu / (1. - 2. * p->nu);  // bri17.hpp:266
+    a.out_scale = p->correction;
+    a.dot_partial = dot_dev ? p->dot_scratch : nullptr;
+    a.herm_n = herm_n;
+    int grid = 0;
+    RS_TRY(bri17b200::axis0::launch(a, dim, p->sm_count, dot_dev ? RED_CTAS : 0, st, &grid));
+    p->fused_launches++;
+    if (dot_dev) cg_finish_kernel<<<1, RED_THREADS, 0, st>>>(p->dot_scratch, grid, dot_dev);
+    mark(p, 4, st);
+    mark(p, 5, st);
+    return BRI17_OK;
+  }
+  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_FORWARD, st));                       // :57 (axis 0)
+  mark(p, 3, st);
   int kb[3] = {0, l.k1_beg[p->rank], 0};
   int ls[3] = {p->shape[0], l.n1_loc, l.S2e};
-  return bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st);
+  if (dot_dev)
+    RS_TRY(bri17_modal_stiffness_apply_dot_f64(p->modal, X, X, kb, ls, 0, p->correction, herm_n, dot_dev,
+                                               p->dot_scratch, RED_CTAS, st));
+  else
+    RS_TRY(bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st));  // :58-92, scale :93-106
+  mark(p, 4, st);
+  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_INVERSE, st));                       // :95
+  mark(p, 5, st);
+  return BRI17_OK;
 }
 
-// Shared CG driver over double arrays; `apply(d, Ad)` is the operator.
+// Shared CG driver over double arrays; `apply(d, Ad, dot)` is the operator, which also leaves this
+// rank's share of <d, A d> in the device scalar `dot`.  The fields hold `nslot/inter` components
+// of `count*inter` doubles (inter = 2: interleaved complex).
 template <typename Apply>
-int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long n, double rtol, int max_iter,
-            int check_every, int *iterations, double *rel_residual, cudaStream_t st) {
+int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long count, int inter, double rtol,
+            int max_iter, int check_every, int *iterations, double *rel_residual, cudaStream_t st) {
+  const int nslot = p->dim * inter;
+  const long long n = count * nslot;
   const size_t bytes = sizeof(double) * std::max<long long>(n, 2);
   if (p->cg_len < bytes) {
     for (double *ptr : {p->cg_r, p->cg_p, p->cg_Ap})
@@ -560,40 +781,43 @@ int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long
     p->cg_len = bytes;
   }
   if (!p->cg_partial) {
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_partial, sizeof(double) * RED_CTAS));
-    BRI17_CUDA_TRY(cudaMalloc(&p->cg_scalars, sizeof(double) * 8));
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_partial, sizeof(double) * std::max(RED_CTAS, 8 * MEAN_CTAS)));
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_scalars, sizeof(double) * 16));
   }
   double *r = p->cg_r, *d = p->cg_p, *Ad = p->cg_Ap;
-  double *sc = p->cg_scalars;  // [0] rr (even iter) [1] rr (odd iter) [2] pAp [3] bb
+  double *sc = p->cg_scalars;  // [0] rr (even iter) [1] rr (odd iter) [2] pAp [8..8+nslot) component sums
   auto reduce_to = [&](double *slot) -> int {
     cg_finish_kernel<<<1, RED_THREADS, 0, st>>>(p->cg_partial, RED_CTAS, slot);
-    if (p->nranks > 1) RS_NCCL_TRY(ncclAllReduce(slot, slot, 1, ncclDouble, ncclSum, p->comm, st));
-    return BRI17_OK;
+    return scalar_allreduce(p, slot, 1, st);
   };
-  const size_t vbytes = sizeof(double) * n;
-  BRI17_CUDA_TRY(cudaMemsetAsync(x, 0, vbytes, st));
-  BRI17_CUDA_TRY(cudaMemcpyAsync(r, b, vbytes, cudaMemcpyDeviceToDevice, st));
-  BRI17_CUDA_TRY(cudaMemcpyAsync(d, b, vbytes, cudaMemcpyDeviceToDevice, st));
-  cg_dot_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(r, r, n, p->cg_partial);
+  // zero-frequency projection of the right-hand side, then r = p = b - mean, x = 0, <r, r>
+  double total = 1.;
+  for (int dd = 0; dd < p->dim; dd++) total *= p->shape[dd];
+  cg_slot_sum_kernel<<<dim3(MEAN_CTAS, nslot), RED_THREADS, 0, st>>>(b, count, inter, p->cg_partial);
+  cg_slot_finish_kernel<<<nslot, RED_THREADS, 0, st>>>(p->cg_partial, sc + 8);
+  RS_TRY(scalar_allreduce(p, sc + 8, nslot, st));
+  cg_init_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(b, x, r, d, count, inter, nslot, sc + 8, 1. / total,
+                                                    p->cg_partial);
   RS_TRY(reduce_to(sc + 0));
   double bb = 0.;
   BRI17_CUDA_TRY(cudaMemcpyAsync(&bb, sc + 0, sizeof(double), cudaMemcpyDeviceToHost, st));
   BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+  if (!std::isfinite(bb)) return fail(BRI17_ERR_BREAKDOWN, "CG: the right-hand side is not finite");
   int it = 0;
   double rr_host = bb;
   if (bb > 0.) {
     for (; it < max_iter;) {
       double *rr = sc + (it & 1), *rr_new = sc + ((it + 1) & 1);
-      RS_TRY(apply(d, Ad));
-      cg_dot_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(d, Ad, n, p->cg_partial);
-      RS_TRY(reduce_to(sc + 2));
-      cg_update_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(x, r, d, Ad, n, rr, sc + 2, p->cg_partial);
+      RS_TRY(apply(d, Ad, sc + 2));
+      RS_TRY(scalar_allreduce(p, sc + 2, 1, st));
+      cg_residual_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(r, Ad, n, rr, sc + 2, p->cg_partial);
       RS_TRY(reduce_to(rr_new));
-      cg_direction_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(d, r, n, rr_new, rr);
+      cg_direction_kernel<<<RED_CTAS, RED_THREADS, 0, st>>>(x, d, r, n, rr, sc + 2, rr_new);
       it++;
       if (check_every > 0 && (it % check_every == 0 || it == max_iter)) {
         BRI17_CUDA_TRY(cudaMemcpyAsync(&rr_host, rr_new, sizeof(double), cudaMemcpyDeviceToHost, st));
         BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!std::isfinite(rr_host)) break;
         if (rr_host <= rtol * rtol * bb) break;
       }
     }
@@ -601,11 +825,16 @@ int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long
       BRI17_CUDA_TRY(cudaMemcpyAsync(&rr_host, sc + (it & 1), sizeof(double), cudaMemcpyDeviceToHost, st));
       BRI17_CUDA_TRY(cudaStreamSynchronize(st));
     }
+  } else {
+    BRI17_CUDA_TRY(cudaStreamSynchronize(st));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(BRI17_ERR_CUDA, std::string("CG: ") + cudaGetErrorString(e));
   if (iterations) *iterations = it;
   if (rel_residual) *rel_residual = bb > 0. ? std::sqrt(rr_host / bb) : 0.;
+  if (!std::isfinite(rr_host))
+    return fail(BRI17_ERR_BREAKDOWN, "CG broke down: the residual norm is not finite after " +
+                                         std::to_string(it) + " iterations");
   return BRI17_OK;
 }
 
@@ -619,7 +848,7 @@ int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long
 // with a barrier after its last read, and the next writer is ordered behind it.
 template <typename LocalFwd, typename LocalInv>
 int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFwd local_fwd, LocalInv local_inv,
-                    cudaStream_t st) {
+                    cudaStream_t st, double *dot_dev) {
   const int dim = p->dim;
   double2 *X = p->W;
   p->timings_valid = false;
@@ -634,22 +863,39 @@ int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFw
   }
   mark(p, 1, st);
   mark(p, 2, st);
-  for (int c = 0; c < dim; c++) {
-    BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
-    RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_FORWARD, st));
+  const bool fused = use_fused(p);
+  if (fused || dot_dev) {
+    // the axis-0 section needs every component: wait for the three forward exchanges
+    for (int c = 0; c < dim; c++) BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
+    RS_TRY(modal_section(p, l, X, st, dot_dev));
+    for (int c = 0; c < dim; c++) {
+      if (c == 0) BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[0], st));
+      BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[0], 0));
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
+      RS_TRY(exchange_barrier(p));
+      BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
+    }
+  } else {
+    for (int c = 0; c < dim; c++) {
+      BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
+      RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_FORWARD, st));
+    }
+    mark(p, 3, st);
+    int kb[3] = {0, l.k1_beg[p->rank], 0};
+    int ls[3] = {p->shape[0], l.n1_loc, l.S2e};
+    if (l.fourier_count)
+      RS_TRY(bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st));
+    mark(p, 4, st);
+    for (int c = 0; c < dim; c++) {
+      RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_INVERSE, st));
+      BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
+      BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
+      RS_TRY(exchange_barrier(p));
+      BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
+    }
+    mark(p, 5, st);
   }
-  mark(p, 3, st);
-  RS_TRY(modal_on_block(p, l, X, st));
-  mark(p, 4, st);
-  for (int c = 0; c < dim; c++) {
-    RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_INVERSE, st));
-    BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
-    BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
-    RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
-    RS_TRY(exchange_barrier(p));
-    BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
-  }
-  mark(p, 5, st);
   mark(p, 6, st);
   for (int c = 0; c < dim; c++) {
     BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
@@ -682,7 +928,6 @@ int bri17_rs_plan_destroy(bri17_rs_plan *p) {
     if (p->peerW[q]) cudaIpcCloseMemHandle(p->peerW[q]);
     if (p->peerW2[q]) cudaIpcCloseMemHandle(p->peerW2[q]);
   }
-  if (p->comm_x) ncclCommDestroy(p->comm_x);
   if (p->comm) ncclCommDestroy(p->comm);
   if (p->sx) cudaStreamDestroy(p->sx);
   for (auto &e : p->ev_a) if (e) cudaEventDestroy(e);
@@ -690,7 +935,8 @@ int bri17_rs_plan_destroy(bri17_rs_plan *p) {
   destroy_layout(p->lc);
   destroy_layout(p->lr);
   for (void *ptr : {(void *)p->W, (void *)p->W2, (void *)p->barrier_word, (void *)p->cg_r, (void *)p->cg_p,
-                    (void *)p->cg_Ap, (void *)p->cg_partial, (void *)p->cg_scalars, (void *)p->rbuf})
+                    (void *)p->cg_Ap, (void *)p->cg_partial, (void *)p->cg_scalars, (void *)p->rbuf,
+                    (void *)p->tabs, (void *)p->twiddle, (void *)p->dot_scratch})
     if (ptr) cudaFree(ptr);
   for (auto &e : p->ev)
     if (e) cudaEventDestroy(e);
@@ -717,6 +963,8 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
   p->rank = rank;
   p->nranks = nranks;
   p->mode = nranks > 1 ? exchange_mode : 0;
+  p->mu = mu;
+  p->nu = nu;
   double cell_volume = 1.0;
   int64_t size = 1;
   for (int d = 0; d < dim; d++) {
@@ -745,6 +993,27 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
   // send/receive pieces (NCCL mode) above it
   p->real_upper = int64_t(dim) * std::max(p->lr.t_count, p->lr.fourier_count);
   if ((rc = setup_layout(p, p->lc))) return bail(rc);
+  cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+
+  // fused axis-0 pass: device copies of the host-built phi|chi|psi tables (bri17.hpp:259-263,
+  // same libm values as the modal plan) and the twiddles of the axis-0 transform
+  if (bri17b200::axis0::supported(shape[0])) {
+    int64_t total = 0;
+    for (int d = 0; d < dim; d++) { p->tab_off[d] = total; total += 3 * int64_t(shape[d]); }
+    std::vector<double> host(total);
+    for (int d = 0; d < dim; d++) {
+      double *t = host.data() + p->tab_off[d];
+      if ((rc = bri17_plan_get_tables(p->modal, d, t, t + shape[d], t + 2 * shape[d], nullptr, nullptr)))
+        return bail(rc);
+    }
+    std::vector<double2> tw(shape[0]);
+    bri17b200::axis0::fill_twiddles(shape[0], tw.data());
+    if (cudaMalloc(&p->tabs, sizeof(double) * total) != cudaSuccess ||
+        cudaMalloc(&p->twiddle, sizeof(double2) * shape[0]) != cudaSuccess ||
+        cudaMemcpy(p->tabs, host.data(), sizeof(double) * total, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->twiddle, tw.data(), sizeof(double2) * shape[0], cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(BRI17_ERR_CUDA, "fused axis-0 tables: allocation/upload failed"));
+  }
 
   if (nranks > 1) {
     ncclUniqueId id;
@@ -754,12 +1023,14 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
     const size_t cap = std::max<size_t>(
         sizeof(double2) * std::max<size_t>(size_t(dim) * size_t(std::max(p->lc.t_count, p->lc.fourier_count)),
                                            2 * size_t(p->real_upper)), 16);
-    if (cudaMalloc(&p->W, cap) != cudaSuccess || cudaMalloc(&p->W2, cap) != cudaSuccess ||
+    const size_t cap_pad = (cap + 255) & ~size_t(255);  // flag page behind the data, 256-byte aligned
+    if (cudaMalloc(&p->W, cap_pad + FLAG_BYTES) != cudaSuccess || cudaMalloc(&p->W2, cap) != cudaSuccess ||
         cudaMalloc(&p->barrier_word, 256) != cudaSuccess)
       return bail(fail(BRI17_ERR_CUDA, "exchange buffer allocation failed"));
     p->buf_bytes = cap;
     cudaMemset(p->barrier_word, 0, 256);
-    {  // exchange stream (high priority), its events and its own communicator
+    cudaMemset(reinterpret_cast<char *>(p->W) + cap_pad, 0, FLAG_BYTES);
+    {  // exchange stream (high priority) and its events
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
       if (cudaStreamCreateWithPriority(&p->sx, cudaStreamNonBlocking, hi) != cudaSuccess)
@@ -768,8 +1039,6 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
         if (cudaEventCreateWithFlags(&p->ev_a[c], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->ev_b[c], cudaEventDisableTiming) != cudaSuccess)
           return bail(fail(BRI17_ERR_CUDA, "cudaEventCreate failed"));
-      nr = ncclCommSplit(p->comm, 0, rank, &p->comm_x, nullptr);
-      if (nr != ncclSuccess) return bail(fail(BRI17_ERR_NCCL, std::string("ncclCommSplit: ") + ncclGetErrorString(nr)));
     }
     if (p->mode == 1) {
       // exchange CUDA-IPC handles of W and W2 through NCCL itself
@@ -797,6 +1066,15 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
         p->peerW[q] = static_cast<double2 *>(a);
         p->peerW2[q] = static_cast<double2 *>(b);
       }
+      p->flags.rank = rank;
+      p->flags.nranks = nranks;
+      for (int q = 0; q < nranks; q++)
+        p->flags.page[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p->peerW[q]) + cap_pad);
+      // nobody may signal before every rank has zeroed its page and mapped the others
+      cudaDeviceSynchronize();
+      nr = ncclAllReduce(p->barrier_word, p->barrier_word, 1, ncclDouble, ncclSum, p->comm, nullptr);
+      if (nr != ncclSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        return bail(fail(BRI17_ERR_NCCL, "plan creation barrier failed"));
     }
   }
   *out = p;
@@ -839,7 +1117,12 @@ int bri17_rs_forward_fft_f64(bri17_rs_plan *p, const void *x_dev, void *x_hat_de
     double2 *X = xh + c0 * l.fourier_count;
     if (p->mode == 1) {  // peers store into our W: stage through it
       RS_TRY(exchange_forward(p, l, p->W2, p->W, nullptr, nc, st));
-      BRI17_CUDA_TRY(cudaMemcpyAsync(X, p->W, sizeof(double2) * nc * l.fourier_count, cudaMemcpyDeviceToDevice, st));
+      if (l.fourier_count)
+        BRI17_CUDA_TRY(cudaMemcpyAsync(X, p->W, sizeof(double2) * nc * l.fourier_count, cudaMemcpyDeviceToDevice, st));
+      // W is free again only once EVERY rank has copied its part out: the next writer of our W
+      // (a peer's exchange kernel, e.g. of a pipelined apply that starts without a barrier) must
+      // be ordered behind this copy
+      RS_TRY(stream_barrier(p, st));
     } else {
       RS_TRY(exchange_forward(p, l, p->W2, X, p->W, nc, st));
     }
@@ -878,11 +1161,19 @@ int bri17_rs_inverse_fft_f64(bri17_rs_plan *p, void *x_hat_dev, void *x_dev, int
   return BRI17_OK;
 }
 
-int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev, void *stream) {
-  if (!p || !u_dev || !F_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
-  if (u_dev == F_dev) return fail(BRI17_ERR_INVALID_ARG, "u_dev and F_dev must be distinct (F is scratch)");
-  DeviceGuard guard(p->device);
-  cudaStream_t st = cudaStream_t(stream);
+}  // extern "C"
+
+namespace {
+
+// A rank whose slab is empty (shape[0] < nranks) passes NULL fields but still takes part in every
+// exchange and barrier, otherwise the other ranks would wait for it forever.
+int check_fields(const bri17_rs_plan *p, const void *a, const void *b) {
+  if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");
+  if (p->real_count > 0 && (!a || !b)) return fail(BRI17_ERR_INVALID_ARG, "NULL field on a rank that owns a non-empty slab");
+  return BRI17_OK;
+}
+
+int apply_complex(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st, double *dot_dev) {
   const Layout &l = p->lc;
   const double2 *u = static_cast<const double2 *>(u_dev);
   double2 *F = static_cast<double2 *>(F_dev);
@@ -890,7 +1181,7 @@ int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev,
   if (p->nranks > 1 && p->mode == 1 && p->pipeline) {
     auto fwd = [&](int c) { return fft_local_c2c(p, u + c * l.t_count, F + c * l.t_count, 1, CUFFT_FORWARD, st); };
     auto inv = [&](int c) { return fft_local_c2c(p, p->W2 + c * l.t_count, F + c * l.t_count, 1, CUFFT_INVERSE, st); };
-    return apply_pipelined(p, l, F, fwd, inv, st);
+    return apply_pipelined(p, l, F, fwd, inv, st, dot_dev);
   }
   p->timings_valid = false;
   mark(p, 0, st);
@@ -902,12 +1193,7 @@ int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev,
     RS_TRY(exchange_forward(p, l, F, p->W, p->W2, dim, st));
   }
   mark(p, 2, st);
-  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_FORWARD, st));                       // :57 (axis 0)
-  mark(p, 3, st);
-  RS_TRY(modal_on_block(p, l, X, st));                                      // :58-92, scale :93-106
-  mark(p, 4, st);
-  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_INVERSE, st));                       // :95
-  mark(p, 5, st);
+  RS_TRY(modal_section(p, l, X, st, dot_dev));                              // :57 (axis 0), :58-106, :95 (axis 0)
   if (p->nranks > 1) {
     if (p->mode == 1) {
       RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));
@@ -928,12 +1214,8 @@ int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev,
 }
 
 // Real fields (plain doubles, [dim][n0_count][N1][(N2)]): r2c over the trailing axes, half
-// spectrum everywhere in between, c2r back.  Same operator as bri17_real_space_apply_f64
-// restricted to real input (what the reference always feeds it, tests/test_bri17.cpp:133-136).
-int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev, void *stream) {
-  if (!p || !u_dev || !F_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
-  DeviceGuard guard(p->device);
-  cudaStream_t st = cudaStream_t(stream);
+// spectrum everywhere in between, c2r back.
+int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st, double *dot_dev) {
   Layout &l = p->lr;
   if (!l.ready) RS_TRY(setup_layout(p, l));
   const int dim = p->dim;
@@ -966,7 +1248,7 @@ int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F
       BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
     return BRI17_OK;
   };
-  if (p->nranks > 1 && p->mode == 1 && p->pipeline) return apply_pipelined(p, l, T, local_fwd, local_inv, st);
+  if (p->nranks > 1 && p->mode == 1 && p->pipeline) return apply_pipelined(p, l, T, local_fwd, local_inv, st, dot_dev);
 
   p->timings_valid = false;
   mark(p, 0, st);
@@ -979,12 +1261,7 @@ int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F
     RS_TRY(exchange_forward(p, l, T, p->W, S, dim, st));
   }
   mark(p, 2, st);
-  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_FORWARD, st));
-  mark(p, 3, st);
-  RS_TRY(modal_on_block(p, l, X, st));
-  mark(p, 4, st);
-  RS_TRY(fft_axis0(p, l, X, dim, CUFFT_INVERSE, st));
-  mark(p, 5, st);
+  RS_TRY(modal_section(p, l, X, st, dot_dev));
   if (p->nranks > 1) {
     if (p->mode == 1) {
       RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));   // peers store into our W2
@@ -1000,13 +1277,44 @@ int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F
   return BRI17_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int bri17_real_space_apply_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev, void *stream) {
+  RS_TRY(check_fields(p, u_dev, F_dev));
+  if (u_dev && u_dev == F_dev) return fail(BRI17_ERR_INVALID_ARG, "u_dev and F_dev must be distinct (F is scratch)");
+  DeviceGuard guard(p->device);
+  return apply_complex(p, u_dev, F_dev, cudaStream_t(stream), nullptr);
+}
+
+// Same operator as bri17_real_space_apply_f64 restricted to real input (what the reference
+// always feeds it, tests/test_bri17.cpp:133-136).
+int bri17_real_space_apply_real_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev, void *stream) {
+  RS_TRY(check_fields(p, u_dev, F_dev));
+  DeviceGuard guard(p->device);
+  return apply_real(p, u_dev, F_dev, cudaStream_t(stream), nullptr);
+}
+
 int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
   if (!p || !key) return fail(BRI17_ERR_INVALID_ARG, "plan/key is NULL");
   if (!std::strcmp(key, "pipeline")) p->pipeline = value != 0;
+  else if (!std::strcmp(key, "fused_axis0")) p->fused = value != 0;
   else if (!std::strcmp(key, "copy_ctas")) {
     if (value < 1) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 1");
     p->copy_ctas = int(value);
   } else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown option ") + key);
+  return BRI17_OK;
+}
+
+int bri17_rs_plan_get_info(const bri17_rs_plan *p, const char *key, int64_t *value) {
+  if (!p || !key || !value) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  if (!std::strcmp(key, "fused_axis0")) *value = use_fused(p) ? 1 : 0;
+  else if (!std::strcmp(key, "fused_launches")) *value = p->fused_launches;
+  else if (!std::strcmp(key, "pipeline")) *value = (p->nranks > 1 && p->mode == 1 && p->pipeline) ? 1 : 0;
+  else if (!std::strcmp(key, "exchange_mode")) *value = p->mode;
+  else if (!std::strcmp(key, "barriers")) *value = int64_t(p->epoch_bar[0] + p->epoch_bar[1]);
+  else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown info key ") + key);
   return BRI17_OK;
 }
 
@@ -1025,26 +1333,72 @@ int bri17_rs_plan_last_timings(bri17_rs_plan *p, double *ms, int n) {
 
 int bri17_cg_solve_f64(bri17_rs_plan *p, const void *b_dev, void *x_dev, double rtol, int max_iter,
                        int check_every, int *iterations, double *rel_residual, void *stream) {
-  if (!p || !b_dev || !x_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  RS_TRY(check_fields(p, b_dev, x_dev));
   if (max_iter < 0) return fail(BRI17_ERR_INVALID_ARG, "max_iter < 0");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
-  const long long n = 2LL * p->dim * p->real_count;  // interleaved complex -> doubles
-  return cg_core(p, [&](const double *d, double *Ad) { return bri17_real_space_apply_f64(p, d, Ad, st); },
-                 static_cast<const double *>(b_dev), static_cast<double *>(x_dev), n, rtol, max_iter,
-                 check_every, iterations, rel_residual, st);
+  // interleaved complex: dim components of real_count (re, im) pairs
+  return cg_core(p, [&](const double *d, double *Ad, double *dot) { return apply_complex(p, d, Ad, st, dot); },
+                 static_cast<const double *>(b_dev), static_cast<double *>(x_dev), p->real_count, 2, rtol,
+                 max_iter, check_every, iterations, rel_residual, st);
 }
 
 int bri17_cg_solve_real_f64(bri17_rs_plan *p, const void *b_dev, void *x_dev, double rtol, int max_iter,
                             int check_every, int *iterations, double *rel_residual, void *stream) {
-  if (!p || !b_dev || !x_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  RS_TRY(check_fields(p, b_dev, x_dev));
   if (max_iter < 0) return fail(BRI17_ERR_INVALID_ARG, "max_iter < 0");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
-  const long long n = (long long)p->dim * p->real_count;
-  return cg_core(p, [&](const double *d, double *Ad) { return bri17_real_space_apply_real_f64(p, d, Ad, st); },
-                 static_cast<const double *>(b_dev), static_cast<double *>(x_dev), n, rtol, max_iter,
-                 check_every, iterations, rel_residual, st);
+  return cg_core(p, [&](const double *d, double *Ad, double *dot) { return apply_real(p, d, Ad, st, dot); },
+                 static_cast<const double *>(b_dev), static_cast<double *>(x_dev), p->real_count, 1, rtol,
+                 max_iter, check_every, iterations, rel_residual, st);
+}
+
+// <u, A u> together with F = A u (what one CG iteration consumes): *dot_host receives the GLOBAL
+// value (summed over ranks).  real_fields = 1: plain double fields through the r2c path.
+int bri17_real_space_apply_dot_f64(bri17_rs_plan *p, const void *u_dev, void *F_dev, int real_fields,
+                                   double *dot_host, void *stream) {
+  RS_TRY(check_fields(p, u_dev, F_dev));
+  if (!dot_host) return fail(BRI17_ERR_INVALID_ARG, "dot_host is NULL");
+  DeviceGuard guard(p->device);
+  cudaStream_t st = cudaStream_t(stream);
+  if (!p->cg_scalars) {
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_partial, sizeof(double) * std::max(RED_CTAS, 8 * MEAN_CTAS)));
+    BRI17_CUDA_TRY(cudaMalloc(&p->cg_scalars, sizeof(double) * 16));
+  }
+  double *slot = p->cg_scalars + 2;
+  RS_TRY(real_fields ? apply_real(p, u_dev, F_dev, st, slot) : apply_complex(p, u_dev, F_dev, st, slot));
+  RS_TRY(scalar_allreduce(p, slot, 1, st));
+  BRI17_CUDA_TRY(cudaMemcpyAsync(dot_host, slot, sizeof(double), cudaMemcpyDeviceToHost, st));
+  BRI17_CUDA_TRY(cudaStreamSynchronize(st));
+  return BRI17_OK;
+}
+
+// Test aid, HOST memory, no device needed: replays the fused axis-0 kernel thread by thread on
+// the CPU.  X: [dim][N0][S] complex, in place.  tabs: phi|chi|psi of axis d at tabs_d ([3][N_d]).
+int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, int k1_begin, int N1, int N2,
+                                 const double *tab0, const double *tab1, const double *tab2, double mu,
+                                 double nu, double out_scale, int hermitian_n, void *X_host, double *dot_out) {
+  if (!X_host || !tab0 || !tab1 || (dim == 3 && !tab2)) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  if (dim != 2 && dim != 3) return fail(BRI17_ERR_INVALID_ARG, "dim must be 2 or 3");
+  if (!bri17b200::axis0::supported(N0)) return fail(BRI17_ERR_UNSUPPORTED, "unsupported N0");
+  std::vector<double2> tw(N0);
+  bri17b200::axis0::fill_twiddles(N0, tw.data());
+  bri17b200::axis0::Params a{};
+  a.X = static_cast<double2 *>(X_host);
+  a.comp_stride = int64_t(N0) * S;
+  a.S = S;
+  a.N0 = N0;
+  a.S2e = dim == 3 ? S2e : 1;
+  a.k1_begin = k1_begin;
+  a.tab0 = tab0; a.tab1 = tab1; a.tab2 = tab2;
+  a.N1 = N1; a.N2 = N2;
+  a.twiddle = tw.data();
+  a.mu = mu;
+  a.scaling = mu / (1. - 2. * nu);
+  a.out_scale = out_scale;
+  a.herm_n = hermitian_n;
+  return bri17b200::axis0::emulate(a, dim, dot_out);
 }
 
 }  // extern "C"

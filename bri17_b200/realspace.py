@@ -70,6 +70,12 @@ class RealSpaceOperator:
     def set_option(self, key, value):
         check(self._lib.bri17_rs_plan_set_option(self._plan, key.encode(), int(value)))
 
+    def info(self, key):
+        """"fused_axis0", "fused_launches", "pipeline", "exchange_mode", "barriers"."""
+        v = C.c_int64()
+        check(self._lib.bri17_rs_plan_get_info(self._plan, key.encode(), C.byref(v)))
+        return v.value
+
     def close(self):
         plan, self._plan = getattr(self, "_plan", None), None
         if plan:
@@ -77,10 +83,15 @@ class RealSpaceOperator:
 
     __del__ = close
 
-    def _check(self, t, shape, what):
+    def _check(self, t, shape, what, dtype=None):
         import torch
-        if tuple(t.shape) != tuple(shape) or t.dtype != torch.complex128:
-            raise ValueError(f"{what}: expected complex128 {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+        dtype = dtype or torch.complex128
+        if tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            raise ValueError(f"{what}: expected {dtype} {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+        if not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"{what}: expected a tensor on cuda:{self.device}, got {t.device}")
+        if not t.is_contiguous():
+            raise ValueError(f"{what}: expected a contiguous tensor")
 
     def apply(self, u, out=None, stream=None):
         """F = (|h|/|N|) iDFT(K^ DFT(u)) on this rank's slab (collective)."""
@@ -97,19 +108,32 @@ class RealSpaceOperator:
         """Same operator on a REAL field, float64 ``(dim, n0_count, N1[, N2])``: r2c
         half-spectrum path (half the FFT, exchange and modal work)."""
         import torch
-        if tuple(u.shape) != tuple(self.real_shape) or u.dtype != torch.float64:
-            raise ValueError(f"u: expected float64 {self.real_shape}")
+        self._check(u, self.real_shape, "u", torch.float64)
         if out is None:
             out = torch.empty_like(u)
+        self._check(out, self.real_shape, "out", torch.float64)
         check(self._lib.bri17_real_space_apply_real_f64(self._plan, _dev_ptr(u), _dev_ptr(out),
                                                         _stream_ptr(stream)))
         return out
 
+    def apply_with_dot(self, u, out=None, stream=None):
+        """``(F, <u, F>)``: the operator and the global scalar product in one go (the Parseval
+        sum is accumulated by the kernel that applies K^).  ``u`` complex128 or float64."""
+        import torch
+        real = u.dtype == torch.float64
+        self._check(u, self.real_shape, "u", u.dtype if real else torch.complex128)
+        if out is None:
+            out = torch.empty_like(u)
+        self._check(out, self.real_shape, "out", u.dtype)
+        dot = C.c_double()
+        check(self._lib.bri17_real_space_apply_dot_f64(self._plan, _dev_ptr(u), _dev_ptr(out), int(real),
+                                                       C.byref(dot), _stream_ptr(stream)))
+        return out, dot.value
+
     def cg_solve_real(self, b, rtol=1e-8, max_iter=1000, check_every=10, stream=None):
         """CG on real float64 fields (see cg_solve)."""
         import torch
-        if tuple(b.shape) != tuple(self.real_shape) or b.dtype != torch.float64:
-            raise ValueError(f"b: expected float64 {self.real_shape}")
+        self._check(b, self.real_shape, "b", torch.float64)
         x = torch.empty_like(b)
         it, res = C.c_int(), C.c_double()
         check(self._lib.bri17_cg_solve_real_f64(self._plan, _dev_ptr(b), _dev_ptr(x), float(rtol),

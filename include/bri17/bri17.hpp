@@ -145,28 +145,47 @@ struct AxisStiffnessFactors {
 // In-place Cholesky factorisation of a real SPD DIM x DIM matrix (lower
 // triangle, row-major) and solve for a complex right-hand side.  Replaces
 // Eigen's K.llt().solve(rhs) of the reference (:341); K^ has zero imaginary
-// part, so the factor is real.
+// part, so the factor is real.  The operation order is the one Eigen 3.3/3.4
+// uses for fixed sizes: llt_inplace<Lower>::unblocked (x = A_kk -
+// A10.squaredNorm(); A21 -= A20 * A10^H; A21 /= x), then the unrolled
+// triangular solves (rhs_i -= (row_i . rhs).sum(); rhs_i /= L_ii).
 template <typename T, int DIM>
 void cholesky_solve(T (&A)[DIM][DIM], std::complex<T> (&x)[DIM]) {
   for (int j = 0; j < DIM; j++) {
     T d = A[j][j];
-    for (int p = 0; p < j; p++) d -= A[j][p] * A[j][p];
+    if (j > 0) {
+      T sq = A[j][0] * A[j][0];
+      for (int p = 1; p < j; p++) sq = sq + A[j][p] * A[j][p];
+      d = d - sq;
+    }
     d = std::sqrt(d);
     A[j][j] = d;
     for (int i = j + 1; i < DIM; i++) {
       T s = A[i][j];
-      for (int p = 0; p < j; p++) s -= A[i][p] * A[j][p];
+      if (j > 0) {
+        T dot = A[i][0] * A[j][0];
+        for (int p = 1; p < j; p++) dot = dot + A[i][p] * A[j][p];
+        s = s - dot;
+      }
       A[i][j] = s / d;
     }
   }
   for (int i = 0; i < DIM; i++) {  // L y = b
     std::complex<T> s = x[i];
-    for (int p = 0; p < i; p++) s -= A[i][p] * x[p];
+    if (i > 0) {
+      std::complex<T> acc = A[i][0] * x[0];
+      for (int p = 1; p < i; p++) acc = acc + A[i][p] * x[p];
+      s = s - acc;
+    }
     x[i] = s / A[i][i];
   }
   for (int i = DIM - 1; i >= 0; i--) {  // L^T x = y
     std::complex<T> s = x[i];
-    for (int p = i + 1; p < DIM; p++) s -= A[p][i] * x[p];
+    if (i < DIM - 1) {
+      std::complex<T> acc = A[i + 1][i] * x[i + 1];
+      for (int p = i + 2; p < DIM; p++) acc = acc + A[p][i] * x[p];
+      s = s - acc;
+    }
     x[i] = s / A[i][i];
   }
 }

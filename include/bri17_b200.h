@@ -34,6 +34,13 @@
  * bri17.hpp:207-211, :241-246).  A plan owns only its per-axis tables and, for
  * the *_host_* entry point, its staging buffers.  Input and output may alias.
  *
+ * Threading: a plan is immutable after creation as far as the device entry
+ * points are concerned (the reference's methods are const and reentrant,
+ * bri17.hpp:212,247); any number of host threads may launch on one plan
+ * concurrently, each on its own stream.  The *_host_* entry point shares one
+ * staging set per plan: concurrent calls on the same plan are serialised by a
+ * mutex inside the plan.  bri17_plan_set_option must not race with launches.
+ *
  * Errors: every function returns BRI17_OK or an error code and never throws;
  * bri17_last_error() returns a thread-local message.  There is no CPU
  * fallback: without a CUDA device plan creation fails with BRI17_ERR_CUDA.
@@ -60,7 +67,8 @@ enum {
   BRI17_ERR_INVALID_ARG = 1, /* bad dim/shape/pointer/alignment: std::invalid_argument in the C++ wrapper */
   BRI17_ERR_CUDA = 2,        /* CUDA runtime failure: std::runtime_error */
   BRI17_ERR_NCCL = 3,        /* NCCL failure (real-space apply only) */
-  BRI17_ERR_UNSUPPORTED = 4
+  BRI17_ERR_UNSUPPORTED = 4,
+  BRI17_ERR_BREAKDOWN = 5    /* iterative solve broke down (non-finite residual): std::runtime_error */
 };
 
 typedef struct bri17_plan bri17_plan;
@@ -82,7 +90,7 @@ BRI17_API void bri17_set_last_error(const char *msg);
  * device `device` (bri17.hpp:54, :193).  dim is 2 or 3.  Builds the per-axis
  * tables phi/chi/psi (bri17.hpp:259-263) and c/s (bri17.hpp:218-221) on the
  * host with libm, in the reference's operation order, and uploads them
- * (3+2 doubles per grid line: K^ itself is never materialised).
+ * (phi/chi/psi, c/s, alpha and sin(alpha) per grid line: K^ itself is never materialised).
  */
 BRI17_API int bri17_plan_create(bri17_plan **out, int dim, const int *shape,
                       const double *L, double mu, double nu, int device);
@@ -128,6 +136,23 @@ BRI17_API int bri17_modal_stiffness_apply_f64(bri17_plan *plan, const void *u_ha
                                     void *f_hat_dev, const int *k_begin,
                                     const int *local_shape, int64_t comp_stride,
                                     double out_scale, void *stream);
+
+/*
+ * bri17_modal_stiffness_apply_f64 that ALSO returns, in the device scalar *dot_dev,
+ *     sum_k w_k Re( u^[k]^H f^[k] )        (f^ including out_scale)
+ * over the block (stream-ordered; deterministic summation order).  By Parseval this is |N| <u, F>
+ * for the real-space fields, so a CG iteration gets <p, A p> from the operator application itself
+ * (tests/test_bri17.cpp:56-107 has no such product; this is what the CG of BASELINE config 5
+ * needs).  hermitian_n = 0: every mode counts once (w_k = 1).  hermitian_n = N > 0: the fastest
+ * axis of the block is the half spectrum k <= N/2 of a real field of length N (K^(N-k) = K^(k)):
+ * modes with 0 < k < N/2 stand for a conjugate pair, w_k = 2.  scratch_dev: scratch_count >= 1
+ * doubles (one partial sum per CTA; the grid is capped at scratch_count, 1184 keeps it full).
+ */
+BRI17_API int bri17_modal_stiffness_apply_dot_f64(bri17_plan *plan, const void *u_hat_dev, void *f_hat_dev,
+                                                  const int *k_begin, const int *local_shape,
+                                                  int64_t comp_stride, double out_scale, int hermitian_n,
+                                                  double *dot_dev, double *scratch_dev, int scratch_count,
+                                                  void *stream);
 
 /*
  * Same operation on HOST buffers: the block is cut along its slowest axis into
@@ -184,6 +209,14 @@ BRI17_API int bri17_eigenstress_to_opposite_strain_f64(bri17_plan *plan, const v
                                                        void *eta_hat_dev, const int *k_begin,
                                                        const int *local_shape, int64_t comp_stride,
                                                        int64_t mode_stride, void *stream);
+/* f^ = tau^ . conj(B^) per mode (bri17.hpp:324-332, :340: the right-hand side of the solve above,
+ * without the solve); nsym -> dim, zero at k = 0.  b = (|h|/|N|) iDFT_unnormalised(f^) is the nodal
+ * force (theory.rst:151-157) of the periodic inclusion problem of python/demo.py:11-23, i.e. the
+ * right-hand side of A x = b that bri17_cg_solve_f64 solves matrix-free (BASELINE config 5). */
+BRI17_API int bri17_eigenstress_to_force_f64(bri17_plan *plan, const void *tau_hat_dev, void *f_hat_dev,
+                                             const int *k_begin, const int *local_shape,
+                                             int64_t tau_comp_stride, int64_t tau_mode_stride,
+                                             int64_t f_comp_stride, int64_t f_mode_stride, void *stream);
 
 /* Frequency multi-index the kernels derive for every linear element of the
  * block: k_out_dev[i*dim + d] (int32).  Uses the same tile cursor as the apply

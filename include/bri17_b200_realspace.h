@@ -60,8 +60,13 @@ BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
 
 /* Tuning knobs: "pipeline" (1 = overlap the exchange of one component with the
  * transforms of the others on a second stream; default 1, fused exchange only),
- * "copy_ctas" (grid cap of the exchange kernel). */
+ * "copy_ctas" (grid cap of the exchange kernel), "fused_axis0" (1 = run FFT(axis 0) ->
+ * K^ -> inverse FFT(axis 0) as one kernel when shape[0] is 16..1024 and a power of two;
+ * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths). */
 BRI17_API int bri17_rs_plan_set_option(bri17_rs_plan *plan, const char *key, int64_t value);
+/* "fused_axis0" (is the fused pass in use), "fused_launches", "pipeline", "exchange_mode",
+ * "barriers" (flag barriers issued so far). */
+BRI17_API int bri17_rs_plan_get_info(const bri17_rs_plan *plan, const char *key, int64_t *value);
 
 /* Geometry of this rank: real-space slab [n0_begin, n0_begin+n0_count) of axis
  * 0, Fourier-space slab [k1_begin, k1_begin+k1_count) of axis 1. */
@@ -74,7 +79,8 @@ BRI17_API int64_t bri17_rs_plan_fourier_count(const bri17_rs_plan *plan);
 /*
  * F = (|h|/|N|) iDFT( K^ DFT(u) )   (tests/test_bri17.cpp:56-107)
  * u_dev, F_dev: [dim][n0_count][N1][(N2)] complex128, distinct buffers; F is
- * also used as scratch.  Collective; asynchronous on `stream`.
+ * also used as scratch.  Collective; asynchronous on `stream`.  A rank whose slab
+ * is empty (shape[0] < nranks) passes NULL fields and must still make the call.
  */
 BRI17_API int bri17_real_space_apply_f64(bri17_rs_plan *plan, const void *u_dev, void *F_dev,
                                          void *stream);
@@ -112,14 +118,27 @@ BRI17_API int bri17_rs_plan_last_timings(bri17_rs_plan *plan, double *ms, int n)
 BRI17_API int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *plan, int real_layout);
 
 /*
+ * F = A u as above AND the global scalar <u, A u> (summed over ranks, written to
+ * *dot_host after a stream synchronisation): the Parseval sum  sum_k Re(u^_k^H f^_k)
+ * is accumulated by the kernel that applies K^, so no extra pass over u and F is
+ * needed.  real_fields: 0 = complex128 fields, 1 = float64 fields (r2c path).
+ */
+BRI17_API int bri17_real_space_apply_dot_f64(bri17_rs_plan *plan, const void *u_dev, void *F_dev,
+                                             int real_fields, double *dot_host, void *stream);
+
+/*
  * Matrix-free conjugate gradients on  A x = b,  A = the real-space operator
- * above (symmetric positive semi-definite; null space = constant fields, so b
- * must have zero mean per component and the solution with zero mean is
- * returned -- the u^(0) = 0 choice of theory.rst:208-212 / bri17.hpp:336-339).
+ * above (symmetric positive semi-definite; null space = constant fields).  The
+ * component means of b are projected out first (K^(0) = 0: the reference skips
+ * the null frequency, bri17.hpp:336-339) and the zero-mean solution is returned
+ * -- the u^(0) = 0 choice of theory.rst:208-212.
  * b_dev, x_dev: real-space slabs (x is overwritten, start from 0).
  * Stops when |r| <= rtol*|b| or after max_iter iterations; all scalars stay
  * on the device (no host synchronisation inside an iteration except every
- * `check_every` iterations for the stopping test).
+ * `check_every` iterations for the stopping test).  Per iteration: one
+ * operator application (which also returns <p, A p>), r -= alpha A p with
+ * <r, r>, then x += alpha p and p = r + beta p in one pass; two scalar
+ * all-reduces.  Returns BRI17_ERR_BREAKDOWN if the residual stops being finite.
  */
 BRI17_API int bri17_cg_solve_f64(bri17_rs_plan *plan, const void *b_dev, void *x_dev, double rtol,
                                  int max_iter, int check_every, int *iterations,
@@ -129,6 +148,16 @@ BRI17_API int bri17_cg_solve_f64(bri17_rs_plan *plan, const void *b_dev, void *x
 BRI17_API int bri17_cg_solve_real_f64(bri17_rs_plan *plan, const void *b_dev, void *x_dev, double rtol,
                                       int max_iter, int check_every, int *iterations,
                                       double *rel_residual, void *stream);
+
+/* Test aid, HOST memory, no device needed: replays the fused axis-0 kernel
+ * (FFT(axis 0) -> K^ * out_scale -> inverse FFT(axis 0)) thread by thread on the CPU,
+ * in place on X_host[dim][N0][S] (complex128).  Column j is (k1, k2) = (k1_begin +
+ * j / S2e, j % S2e) in 3-D, k1 = k1_begin + j in 2-D.  tab_d: phi|chi|psi of axis d
+ * ([3][N_d], bri17_plan_get_tables).  dot_out (optional): sum_k w_k Re(u^H f). */
+BRI17_API int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, int k1_begin, int N1,
+                                           int N2, const double *tab0, const double *tab1,
+                                           const double *tab2, double mu, double nu, double out_scale,
+                                           int hermitian_n, void *X_host, double *dot_out);
 
 #ifdef __cplusplus
 }

@@ -269,10 +269,16 @@ void oracle_apply_strain_displacement(int dim, const int *shape,
  * tau, eta: nsym complex numbers (Mandel notation), interleaved.
  *
  * PARITY UNPINNED: the reference solves K u = rhs with Eigen's K.llt().solve()
- * (:341); Eigen is neither vendored nor installed and no reference test calls
- * this method (only python/demo.py does).  The LLT solve is restated as the
- * textbook Cholesky factorisation K = L L^T (column by column, L real because
- * Im K = 0) followed by forward and backward substitution.
+ * (:341); Eigen (>= 3.3, no version pin) is neither vendored nor installed and no
+ * reference test calls this method (only python/demo.py does).  The solve is
+ * restated in the operation order Eigen 3.3/3.4 publishes for fixed sizes < 32:
+ * Cholesky/LLT.h llt_inplace<Scalar,Lower>::unblocked (x = A_kk - A10.squaredNorm();
+ * A21 -= A20 * A10^H; A21 /= x) followed by matrixL().solveInPlace and
+ * matrixU().solveInPlace through SolveTriangular.h triangular_solver_unroller
+ * (rhs_i -= (row_i . rhs).sum(); rhs_i /= L_ii).  K^ is real (Im K = 0), so the
+ * factor is real; a complex number divided by (L_ii + 0i) under GCC's __divdc3
+ * equals the component-wise real division used here.  What stays unpinned: the
+ * Eigen version and the user's compiler flags (FMA contraction, vectorised pmadd).
  * out_u (may be NULL) receives the intermediate displacement u (DIM complex).
  */
 void oracle_modal_eigenstress_to_opposite_strain(int dim, const int *shape, const double *L,
@@ -318,25 +324,44 @@ void oracle_modal_eigenstress_to_opposite_strain(int dim, const int *shape, cons
   double A[3][3];
   for (int i = 0; i < dim; i++)
     for (int j = 0; j < dim; j++) A[i][j] = Kf[2 * (dim * i + j)];
+  /* llt_inplace<Lower>::unblocked: x = A_kk - A10.squaredNorm(); A21 -= A20 * A10^H; A21 /= x */
   for (int j = 0; j < dim; j++) {
     double d = A[j][j];
-    for (int p = 0; p < j; p++) d -= A[j][p] * A[j][p];
+    if (j > 0) {
+      double sq = A[j][0] * A[j][0];
+      for (int p = 1; p < j; p++) sq = sq + A[j][p] * A[j][p];
+      d = d - sq;
+    }
     d = sqrt(d);
     A[j][j] = d;
     for (int i = j + 1; i < dim; i++) {
       double t = A[i][j];
-      for (int p = 0; p < j; p++) t -= A[i][p] * A[j][p];
+      if (j > 0) {
+        double dot = A[i][0] * A[j][0];
+        for (int p = 1; p < j; p++) dot = dot + A[i][p] * A[j][p];
+        t = t - dot;
+      }
       A[i][j] = t / d;
     }
   }
+  /* matrixL().solveInPlace: x_i = (x_i - sum_p L_ip x_p) / L_ii, the sum formed first */
   for (int i = 0; i < dim; i++) {
     double sr = ur[i], si = ui[i];
-    for (int p = 0; p < i; p++) { sr -= A[i][p] * ur[p]; si -= A[i][p] * ui[p]; }
+    if (i > 0) {
+      double ar = A[i][0] * ur[0], ai = A[i][0] * ui[0];
+      for (int p = 1; p < i; p++) { ar = ar + A[i][p] * ur[p]; ai = ai + A[i][p] * ui[p]; }
+      sr = sr - ar; si = si - ai;
+    }
     ur[i] = sr / A[i][i]; ui[i] = si / A[i][i];
   }
+  /* matrixU().solveInPlace (U = L^H), last row first, sums over increasing column index */
   for (int i = dim - 1; i >= 0; i--) {
     double sr = ur[i], si = ui[i];
-    for (int p = i + 1; p < dim; p++) { sr -= A[p][i] * ur[p]; si -= A[p][i] * ui[p]; }
+    if (i < dim - 1) {
+      double ar = A[i + 1][i] * ur[i + 1], ai = A[i + 1][i] * ui[i + 1];
+      for (int p = i + 2; p < dim; p++) { ar = ar + A[p][i] * ur[p]; ai = ai + A[p][i] * ui[p]; }
+      sr = sr - ar; si = si - ai;
+    }
     ur[i] = sr / A[i][i]; ui[i] = si / A[i][i];
   }
   if (out_u) for (int i = 0; i < dim; i++) { out_u[2 * i] = ur[i]; out_u[2 * i + 1] = ui[i]; }

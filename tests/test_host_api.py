@@ -149,8 +149,20 @@ def test_error_behaviour():
         hooke.modal_stiffness_matrix(k, np.empty(8, dtype=np.complex128)[::2])
     with pytest.raises(ValueError):
         hooke.modal_stiffness_matrix(k, K.reshape(2, 2))
-    with pytest.raises(ValueError):          # frequency outside [0, N)
-        hooke.modal_stiffness_matrix(np.array([0, 4], dtype=np.intc), K)
+    # the reference never bound-checks k (bri17.hpp:247) and K^ is N-periodic in k: indices outside
+    # [0, N) are accepted and wrapped; any integer sequence converts like pybind11's array_t<int>
+    K2 = np.empty(4, dtype=np.complex128)
+    hooke.modal_stiffness_matrix(np.array([1, 3], dtype=np.intc), K)
+    hooke.modal_stiffness_matrix([5, -1], K2)
+    assert np.array_equal(K, K2)
+    hooke.modal_stiffness_matrix(np.array([1, 3], dtype=np.int64), K2)
+    assert np.array_equal(K, K2)
+    with pytest.raises(ValueError):          # k must be one-dimensional, of length dim
+        hooke.modal_stiffness_matrix(np.zeros((2, 1), dtype=np.intc), K)
+    with pytest.raises(ValueError):
+        hooke.modal_stiffness_matrix(np.array([0.5, 1.0]), K)
+    with pytest.raises(ValueError):          # B^ uses half angles, not N-periodic: outside [0, N) is refused
+        hooke.modal_strain_displacement(np.array([0, 4], dtype=np.intc), np.empty(2, dtype=np.complex128))
     with pytest.raises(TypeError):           # 3-D grid into a 2-D Hooke (template mismatch)
         b.Hooke2f64(1.0, 0.3, b.CartesianGrid3f64((2, 2, 2), (1., 1., 1.)))
     lib = _lib.load()
