@@ -1100,7 +1100,10 @@ int64_t bri17_rs_plan_exchange_bytes(const bri17_rs_plan *p, int real_layout) {
 }
 
 int bri17_rs_forward_fft_f64(bri17_rs_plan *p, const void *x_dev, void *x_hat_dev, int ncomp, void *stream) {
-  if (!p || !x_dev || !x_hat_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");
+  // a rank without rows (or without k1 columns) passes NULL on that side and still takes part
+  if ((p->lc.t_count > 0 && !x_dev) || (p->lc.fourier_count > 0 && !x_hat_dev))
+    return fail(BRI17_ERR_INVALID_ARG, "NULL field on a rank that owns a non-empty slab");
   if (ncomp < 1) return fail(BRI17_ERR_INVALID_ARG, "ncomp < 1");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
@@ -1132,7 +1135,9 @@ int bri17_rs_forward_fft_f64(bri17_rs_plan *p, const void *x_dev, void *x_hat_de
 }
 
 int bri17_rs_inverse_fft_f64(bri17_rs_plan *p, void *x_hat_dev, void *x_dev, int ncomp, double scale, void *stream) {
-  if (!p || !x_dev || !x_hat_dev) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  if (!p) return fail(BRI17_ERR_INVALID_ARG, "plan is NULL");
+  if ((p->lc.t_count > 0 && !x_dev) || (p->lc.fourier_count > 0 && !x_hat_dev))
+    return fail(BRI17_ERR_INVALID_ARG, "NULL field on a rank that owns a non-empty slab");
   if (ncomp < 1) return fail(BRI17_ERR_INVALID_ARG, "ncomp < 1");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);

@@ -314,3 +314,202 @@ def test_large_3d_512_sampled_slabs(oracle_mod):
     # slabs reproduce the full-grid result bit for bit (what each GPU computes at N>1)
     fs2 = op.apply_modal_stiffness(u[:, 448:512].contiguous(), k_begin=(448, 0, 0))
     assert torch.equal(torch.view_as_real(fs2), torch.view_as_real(f[:, 448:512]))
+
+
+# ---------------------------------------------------------------------------
+# round 2: inclusion right-hand side, Parseval sum, reentrancy, 64-bit offsets
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(6, 8), (6, 8, 5), (5, 4, 300), (3, 700)])
+def test_eigenstress_to_force_vs_definition(oracle_mod, shape):
+    """f^ = tau^ . conj(B^) (bri17.hpp:324-332, :340) per mode against numpy on the oracle's B^."""
+    dim = len(shape)
+    nsym = dim * (dim + 1) // 2
+    L = spacing_L(shape)
+    o = oracle_mod.best()
+    rng = np.random.default_rng(12)
+    tau = rng.standard_normal((nsym,) + shape) + 1j * rng.standard_normal((nsym,) + shape)
+    op = b.ModalOperator(shape, L, MU, NU)
+    f = op.eigenstress_to_force(to_dev(tau)).cpu().numpy()
+    pairs = [(0, 0), (1, 1), (0, 1)] if dim == 2 else [(0, 0), (1, 1), (2, 2), (1, 2), (2, 0), (0, 1)]
+    ref = np.zeros((dim,) + shape, dtype=complex)
+    for k in np.ndindex(*shape):
+        if not any(k):
+            continue                                        # :336-339: zero at the null frequency
+        sl = (slice(None),) + k
+        B = o.modal_strain_displacement(shape, L, k)
+        T = np.zeros((dim, dim), dtype=complex)
+        for s, (p, q) in enumerate(pairs):
+            T[p, q] = T[q, p] = tau[sl][s] if p == q else tau[sl][s] / np.sqrt(2.0)
+        ref[sl] = T @ B.conj()
+    scale = np.abs(ref).max(axis=0)
+    err = np.abs(f - ref).max(axis=0)
+    assert np.all(f[(slice(None),) + (0,) * dim] == 0)
+    assert (err <= 1e-12 * np.maximum(scale, np.abs(tau).max(axis=0) * 1e-3)).all()
+    # and K^-1 of it is the displacement of the one-pass direct solve
+    u1 = op.solve_modal_stiffness(op.eigenstress_to_force(to_dev(tau))).cpu().numpy()
+    u2 = op.eigenstress_to_displacement(to_dev(tau)).cpu().numpy()
+    assert np.abs(u1 - u2).max() <= 1e-11 * np.abs(u2).max()
+
+
+@pytest.mark.parametrize("shape,herm", [((16, 12, 10), 0), ((8, 8, 33), 64), ((5, 7, 600), 0), ((64, 33), 64),
+                                        ((3, 4, 5), 8), ((2, 4097), 0)])
+def test_apply_with_parseval_sum(oracle_mod, shape, herm):
+    """bri17_modal_stiffness_apply_dot_f64: same f^ bit for bit, plus sum_k w_k Re(u^H f^)."""
+    dim = len(shape)
+    full = shape[:-1] + ((herm or shape[-1]),)             # the grid; the block keeps k_last < shape[-1]
+    L = spacing_L(full)
+    u = oracle_mod.synthetic_u_hat(dim, shape, seed=5)
+    op = b.ModalOperator(full, L, MU, NU)
+    ud = to_dev(u)
+    f_plain = op.apply_modal_stiffness(ud, out_scale=0.25)
+    f, dot = op.apply_modal_stiffness_dot(ud, out_scale=0.25, hermitian_n=herm)
+    assert torch.equal(f, f_plain)
+    fn = f.cpu().numpy()
+    w = np.ones(shape[-1])
+    if herm:
+        k = np.arange(shape[-1])
+        w = np.where((k == 0) | (2 * k == herm), 1.0, 2.0)
+    expect = float(np.sum(w * np.real(np.conj(u) * fn)))
+    assert abs(dot - expect) <= 1e-12 * abs(expect)
+    _, dot2 = op.apply_modal_stiffness_dot(ud, out_scale=0.25, hermitian_n=herm)
+    assert dot2 == dot                                      # deterministic summation order
+
+
+def test_plan_is_reentrant_two_threads(oracle_mod):
+    """plans are immutable after creation -> two host threads launch on ONE plan
+    concurrently (own streams, own buffers); results stay bit-identical to the oracle.  The
+    host-buffer entry point shares one staging set per plan and serialises internally."""
+    import threading
+    shape = (24, 20, 130)
+    L = spacing_L(shape)
+    op = b.ModalOperator(shape, L, MU, NU)
+    o = oracle_mod.best()
+    us = [oracle_mod.synthetic_u_hat(3, shape, seed=70 + t) for t in range(2)]
+    refs = [o.apply_modal_stiffness(shape, L, MU, NU, u) for u in us]
+    errors = []
+
+    def device_worker(t):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                ud = to_dev(us[t])
+                out = torch.empty_like(ud)
+                for _ in range(200):
+                    op.apply_modal_stiffness(ud, out=out, stream=s)
+                s.synchronize()
+                if not np.array_equal(out.cpu().numpy(), refs[t]):
+                    errors.append(f"device thread {t}: result differs")
+        except Exception as e:       # noqa: BLE001
+            errors.append(repr(e))
+
+    def host_worker(t):
+        try:
+            for _ in range(10):
+                f = op.apply_modal_stiffness_host(us[t])
+                if not np.array_equal(f, refs[t]):
+                    errors.append(f"host thread {t}: result differs")
+        except Exception as e:       # noqa: BLE001
+            errors.append(repr(e))
+
+    for worker in (device_worker, host_worker):
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+    assert not errors, errors
+    assert op.info("launches") >= 400
+
+
+def _free_gib():
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2**30
+
+
+def _check_planes(oracle_mod, op, shape, L, u_planes, f, planes):
+    """Sampled k0 planes of an (in-place) result against the compiled reference."""
+    o = oracle_mod.best()
+    dim = len(shape)
+    for a, u in zip(planes, u_planes):
+        ref = o.apply_modal_stiffness(shape, L, MU, NU, u, k_begin=(a,) + (0,) * (dim - 1))
+        got = f[:, a:a + 1].cpu().numpy()
+        assert per_mode_rel_err(got, ref) <= TOL, a
+        assert np.array_equal(got, ref), a
+
+
+def test_1024_cubed_in_place_offsets_beyond_2_31(oracle_mod):
+    """BASELINE config 4's grid on ONE GPU, in place (48 GiB): element offsets of component 2
+    exceed 2^31 (the reference's `int` indexing overflows there, tests/test_bri17.cpp:83,87);
+    both mappings; index map of slabs at the far end; sampled planes against oracle/_ref."""
+    if _free_gib() < 60:
+        pytest.skip("needs 60 GiB of free device memory")
+    shape = (1024, 1024, 1024)
+    L = spacing_L(shape)
+    op = b.ModalOperator(shape, L, MU, NU)
+    planes = [0, 511, 1023]
+    for mapping in (1, 2):
+        op.set_option("mapping", mapping)
+        g = torch.Generator(device="cuda").manual_seed(1024 + mapping)
+        u = torch.view_as_complex(torch.randn((3,) + shape + (2,), dtype=torch.float64, device="cuda",
+                                              generator=g))
+        keep = [u[:, a:a + 1].cpu().numpy() for a in planes]
+        op.apply_modal_stiffness(u, out=u)                      # in place
+        assert op.info("last_flat") == (mapping == 2)
+        _check_planes(oracle_mod, op, shape, L, keep, u, planes)
+        for kb, local in (((1020, 0, 0), (4, 1024, 1024)), ((1023, 1000, 0), (1, 24, 1024))):
+            k = op.freq_index_map(local, kb).cpu().numpy()
+            assert np.array_equal(k, oracle_mod.freq_index_map(kb, local))
+        del u
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("shape", [(2049, 1024, 1024), (65536, 32769)])
+def test_block_larger_than_2_31_modes(oracle_mod, shape):
+    """More than 2^31 - 1 modes in ONE block: the flat mapping's 64-bit index branch
+    (flat_index) and 64-bit tile counters, in place (96 / 64 GiB).  Sampled planes against
+    oracle/_ref and the index map across the 2^31 boundary."""
+    dim = len(shape)
+    modes = int(np.prod(shape, dtype=np.int64))
+    assert modes > 2**31
+    need = modes * 16 * dim / 2**30
+    if _free_gib() < need + 30:
+        pytest.skip(f"needs {need + 30:.0f} GiB of free device memory")
+    L = spacing_L(shape)
+    op = b.ModalOperator(shape, L, MU, NU)
+    op.set_option("mapping", 2)
+    g = torch.Generator(device="cuda").manual_seed(31)
+    u = torch.view_as_complex(torch.randn((dim,) + shape + (2,), dtype=torch.float64, device="cuda",
+                                          generator=g))
+    planes = [0, shape[0] // 2, shape[0] - 1]
+    keep = [u[:, a:a + 1].cpu().numpy() for a in planes]
+    op.apply_modal_stiffness(u, out=u)
+    assert op.info("last_flat") == 1
+    _check_planes(oracle_mod, op, shape, L, keep, u, planes)
+    del u
+    torch.cuda.empty_cache()
+    # index map of the whole block (int32 [modes][dim]): windows at both ends and across 2^31
+    k = op.freq_index_map()
+    plane = modes // shape[0]
+    for a in (0, 2**31 // plane - 1, shape[0] - 2):
+        local = (2,) + shape[1:]
+        kb = (a,) + (0,) * (dim - 1)
+        got = k[a * plane:(a + 2) * plane].cpu().numpy()
+        assert np.array_equal(got, oracle_mod.freq_index_map(kb, local)), a
+    del k
+    torch.cuda.empty_cache()
+
+
+def test_field_writers_large(oracle_mod):
+    """Mode-major B^ / K^ fields (smem-staged writers) on rows that span several tiles and on
+    rows shorter than a tile; per-mode comparison with the oracle."""
+    for shape in ((4, 3, 700), (6, 5, 33), (5, 1000), (7, 3)):
+        dim = len(shape)
+        L = spacing_L(shape)
+        o = oracle_mod.best()
+        op = b.ModalOperator(shape, L, MU, NU)
+        Bf = op.modal_strain_displacement_field().cpu().numpy()
+        Kf = op.modal_stiffness_field().cpu().numpy()
+        for k in list(np.ndindex(*shape))[::7]:
+            Bref = o.modal_strain_displacement(shape, L, k)
+            assert np.abs(Bf[k] - Bref).max() <= 1e-12 * max(np.abs(Bref).max(), 1e-300) + 1e-15
+            assert np.array_equal(Kf[k], o.modal_stiffness(shape, L, MU, NU, k))

@@ -144,11 +144,108 @@ def test_cg_solves_the_periodic_problem(oracle_mod, shape):
     assert np.abs(x - direct).max() <= 1e-7 * np.abs(direct).max()
 
 
+@pytest.mark.parametrize("shape", [(16, 12, 10), (32, 32, 32), (64, 12, 10), (128, 6, 5), (256, 4, 6),
+                                   (512, 3, 4), (1024, 2, 3), (64, 64), (16, 9)])
+def test_fused_axis0_pass_equals_cufft_path(oracle_mod, shape):
+    """The one-kernel FFT(axis 0) -> K^ -> iFFT(axis 0) pass (every supported length, both
+    field types) against the cuFFT + modal kernel + cuFFT path and the numpy restatement."""
+    dim = len(shape)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(17)
+    u = rng.standard_normal((dim,) + shape)
+    ref = real_space_apply_ref(oracle_mod.best(), shape, L, MU, NU, u + 0j)
+    op = RealSpaceOperator(shape, L, MU, NU)
+    assert op.info("fused_axis0") == 1
+    uc, ur = torch.from_numpy(u + 0j).cuda(), torch.from_numpy(u).cuda()
+    Fc, Fr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
+    assert op.info("fused_launches") == 2
+    op.set_option("fused_axis0", 0)
+    assert op.info("fused_axis0") == 0
+    Gc, Gr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
+    assert op.info("fused_launches") == 2
+    scale = np.abs(ref).max()
+    for got in (Fc, Gc):
+        assert np.abs(got - ref).max() <= 1e-13 * scale
+    for got in (Fr, Gr):
+        assert np.abs(got - ref.real).max() <= 1e-13 * scale
+    assert np.abs(Fc - Gc).max() <= 1e-13 * scale and np.abs(Fr - Gr).max() <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("shape", [(16, 12, 10), (9, 6, 7), (64, 33), (12, 10)])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_apply_with_dot(oracle_mod, shape, fused):
+    """F = A u and <u, A u> in one go (Parseval sum inside the K^ kernel), complex and real
+    fields, fused and cuFFT axis-0 paths, against the plain scalar product of the fields."""
+    dim = len(shape)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(23)
+    u = rng.standard_normal((dim,) + shape)
+    op = RealSpaceOperator(shape, L, MU, NU)
+    op.set_option("fused_axis0", fused)
+    ur = torch.from_numpy(u).cuda()
+    F, dot = op.apply_with_dot(ur)
+    assert torch.equal(F, op.apply_real(ur))
+    expect = float((ur * F).sum())
+    assert expect > 0 and abs(dot - expect) <= 1e-12 * expect
+    v = rng.standard_normal((dim,) + shape) + 1j * rng.standard_normal((dim,) + shape)
+    vc = torch.from_numpy(v).cuda()
+    G, dotc = op.apply_with_dot(vc)
+    assert torch.equal(G, op.apply(vc))
+    expect = float((vc.conj() * G).sum().real)
+    assert abs(dotc - expect) <= 1e-12 * expect
+
+
+def test_cg_projects_out_the_null_space(oracle_mod):
+    """K^(0) = 0 (bri17.hpp:336-339, theory.rst:208-212): a right-hand side with a non-zero
+    mean is projected, CG converges to the zero-mean solution instead of drifting."""
+    shape = (16, 12, 10)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(9)
+    x_true = rng.standard_normal((3,) + shape)
+    x_true -= x_true.mean(axis=(1, 2, 3), keepdims=True)
+    b = real_space_apply_ref(oracle_mod.best(), shape, L, MU, NU, x_true + 0j).real
+    shift = np.array([0.3, -1.7, 2.5]).reshape(3, 1, 1, 1) * np.abs(b).max()
+    op = RealSpaceOperator(shape, L, MU, NU)
+    x, iters, res = op.cg_solve_real(torch.from_numpy(np.ascontiguousarray(b + shift)).cuda(), rtol=1e-11,
+                                     max_iter=2000, check_every=5)
+    assert res <= 1e-11 and 0 < iters < 2000
+    assert np.abs(x.cpu().numpy() - x_true).max() <= 1e-7 * np.abs(x_true).max()
+    xc, _, resc = op.cg_solve(torch.from_numpy(b + shift + 1j * shift).cuda(), rtol=1e-11, max_iter=2000,
+                              check_every=5)
+    assert resc <= 1e-11
+    assert np.abs(xc.cpu().numpy() - x_true).max() <= 1e-7 * np.abs(x_true).max()
+    # a constant right-hand side is entirely in the null space: zero iterations, x = 0
+    x0, it0, res0 = op.cg_solve_real(torch.ones((3,) + shape, dtype=torch.float64, device="cuda"))
+    assert it0 == 0 and res0 == 0.0 and float(x0.abs().max()) == 0.0
+
+
+def test_inclusion_problem_cg_vs_direct_solve(oracle_mod):
+    """BASELINE config 5 in small: the periodic inclusion problem of python/demo.py:11-23
+    (eigenstress patch [0, N/8)^3, tau_in = last Mandel component).  Right-hand side from
+    tau^ . conj(B^) (bri17.hpp:340), matrix-free CG on real fields to rtol 1e-10, against the
+    one-pass per-mode direct solve (bri17.hpp:341)."""
+    import bri17_b200 as b
+    shape, L = (64, 64, 64), (1.0, 1.0, 1.0)
+    mu, nu = 1.0, 0.3                                              # python/demo.py:13-14
+    rs = RealSpaceOperator(shape, L, mu, nu)
+    op = b.ModalOperator(shape, L, mu, nu)
+    tau = torch.zeros((6,) + shape, dtype=torch.complex128, device="cuda")
+    tau[-1, :8, :8, :8] = 1.0                                      # python/demo.py:16-23
+    tau_hat = rs.forward_fft(tau)
+    f_hat = op.eigenstress_to_force(tau_hat)
+    u_direct = rs.inverse_fft(op.eigenstress_to_displacement(tau_hat)).real
+    h_vol = float(np.prod([l / n for l, n in zip(L, shape)]))
+    b_real = rs.inverse_fft(f_hat, scale=h_vol / float(np.prod(shape))).real.contiguous()
+    x, iters, res = rs.cg_solve_real(b_real, rtol=1e-10, max_iter=5000, check_every=10)
+    assert res <= 1e-10 and iters < 5000
+    assert float((x - u_direct).abs().max()) <= 1e-6 * float(u_direct.abs().max())
+
+
 def test_multi_gpu_realspace():
-    """World-size-2 run of tests/dist_gpu_worker.py (both exchange modes)."""
+    """Every-GPU run of tests/dist_gpu_worker.py (both exchange modes)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    world = min(torch.cuda.device_count(), 4)
+    world = torch.cuda.device_count()
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
