@@ -21,17 +21,17 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) axis0_fused_kernel(const 
   __syncthreads();
   double dot = 0.;
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const long long col0 = tile * C::W;
-    phase<C, DIM, 0>(tid, data, tw, p, col0, dot);
+    const long long col0 = tile * C::W, nx = (tile + gridDim.x) * C::W;
+    phase<C, DIM, 0>(tid, data, tw, p, col0, nx, dot);
     __syncthreads();
-    phase<C, DIM, 1>(tid, data, tw, p, col0, dot);
+    phase<C, DIM, 1>(tid, data, tw, p, col0, nx, dot);
     __syncthreads();
-    phase<C, DIM, 2>(tid, data, tw, p, col0, dot);
+    phase<C, DIM, 2>(tid, data, tw, p, col0, nx, dot);
     __syncthreads();
     if constexpr (C::NPH > 3) {
-      phase<C, DIM, 3>(tid, data, tw, p, col0, dot);
+      phase<C, DIM, 3>(tid, data, tw, p, col0, nx, dot);
       __syncthreads();
-      phase<C, DIM, 4>(tid, data, tw, p, col0, dot);
+      phase<C, DIM, 4>(tid, data, tw, p, col0, nx, dot);
       __syncthreads();
     }
   }
@@ -98,26 +98,49 @@ int launch(Params p, int dim, int sm_count, int max_grid, cudaStream_t st, int *
   return fail(BRI17_ERR_UNSUPPORTED, "fused axis-0 pass: unsupported N0");
 }
 
-// exp(-2 pi i j / N0), j < N0, evaluated in the first octant and mirrored (libm, host).
-void fill_twiddles(int N0, double2 *tw) {
+// exp(-2 pi i q / N0) for 0 <= q < N0, evaluated in the first octant and mirrored (libm, host).
+static double2 unit_root(int N0, int q) {
   const double two_pi = 6.283185307179586476925286766559;
-  for (int j = 0; j < N0; j++) {
-    // reduce to the angle of j' in [0, N0/8] by symmetry so that cos/sin see small arguments
-    int q = j % N0;
-    const int oct = (8 * q) / N0;           // octant 0..7
-    double c, s;
-    auto cs = [&](int jj, double &cc, double &ss) { const double a = two_pi * jj / N0; cc = std::cos(a); ss = std::sin(a); };
-    switch (oct) {
-      case 0: cs(q, c, s); break;
-      case 1: { double cc, ss; cs(N0 / 4 - q, cc, ss); c = ss; s = cc; } break;
-      case 2: { double cc, ss; cs(q - N0 / 4, cc, ss); c = -ss; s = cc; } break;
-      case 3: { double cc, ss; cs(N0 / 2 - q, cc, ss); c = -cc; s = ss; } break;
-      case 4: { double cc, ss; cs(q - N0 / 2, cc, ss); c = -cc; s = -ss; } break;
-      case 5: { double cc, ss; cs(3 * N0 / 4 - q, cc, ss); c = -ss; s = -cc; } break;
-      case 6: { double cc, ss; cs(q - 3 * N0 / 4, cc, ss); c = ss; s = -cc; } break;
-      default: { double cc, ss; cs(N0 - q, cc, ss); c = cc; s = -ss; } break;
-    }
-    tw[j] = make_double2(c, -s);
+  const int oct = (8 * q) / N0;  // octant 0..7
+  double c, s, cc, ss;
+  auto cs = [&](int jj, double &co, double &si) { const double a = two_pi * jj / N0; co = std::cos(a); si = std::sin(a); };
+  switch (oct) {
+    case 0: cs(q, c, s); break;
+    case 1: cs(N0 / 4 - q, cc, ss); c = ss; s = cc; break;
+    case 2: cs(q - N0 / 4, cc, ss); c = -ss; s = cc; break;
+    case 3: cs(N0 / 2 - q, cc, ss); c = -cc; s = ss; break;
+    case 4: cs(q - N0 / 2, cc, ss); c = -cc; s = -ss; break;
+    case 5: cs(3 * N0 / 4 - q, cc, ss); c = -ss; s = -cc; break;
+    case 6: cs(q - 3 * N0 / 4, cc, ss); c = ss; s = -cc; break;
+    default: cs(N0 - q, cc, ss); c = cc; s = -ss; break;
+  }
+  return make_double2(c, -s);
+}
+
+template <class C>
+static void fill_cfg(double2 *tw) {
+  for (int i = 0; i < C::N0; i++) tw[i] = make_double2(1., 0.);
+  constexpr int s0 = C::N0 / C::R0;  // stage 0: block N0, stride s0, twiddle w_N0^(j m)
+  for (int m = 1; m < C::R0; m++)
+    for (int j = 0; j < s0; j++) tw[(m - 1) * s0 + j] = unit_root(C::N0, j * m);
+  if constexpr (C::NS == 3) {  // stage 1: block N0/R0, stride s1, twiddle w_{N0/R0}^(j m) = w_N0^(j m R0)
+    constexpr int s1 = C::N0 / (C::R0 * C::R1);
+    static_assert(C::TW1 + (C::R1 - 1) * s1 <= C::N0, "twiddle table overflows N0 entries");
+    for (int m = 1; m < C::R1; m++)
+      for (int j = 0; j < s1; j++) tw[C::TW1 + (m - 1) * s1 + j] = unit_root(C::N0, j * m * C::R0);
+  }
+}
+
+// Per-stage twiddle tables of the plan for N0 (layout: Cfg), N0 complex in all.
+void fill_twiddles(int N0, double2 *tw) {
+  switch (N0) {
+    case 16: fill_cfg<Cfg16>(tw); break;
+    case 32: fill_cfg<Cfg32>(tw); break;
+    case 64: fill_cfg<Cfg64>(tw); break;
+    case 128: fill_cfg<Cfg128>(tw); break;
+    case 256: fill_cfg<Cfg256>(tw); break;
+    case 512: fill_cfg<Cfg512>(tw); break;
+    case 1024: fill_cfg<Cfg1024>(tw); break;
   }
 }
 

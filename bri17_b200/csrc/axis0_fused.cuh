@@ -54,7 +54,7 @@ struct Params {
   int k1_begin;            // global index of the first k1 (axis-1 frequency) of the block
   const double *tab0, *tab1, *tab2;  // per-axis phi|chi|psi, [3][N_d] (tab2 unused in 2-D)
   int N1, N2;              // table lengths of axes 1 and 2
-  const double2 *twiddle;  // exp(-2 pi i j / N0), j < N0
+  const double2 *twiddle;  // per-stage twiddle tables (fill_twiddles), N0 complex
   double mu, scaling, out_scale;
   double *dot_partial;     // optional: one partial sum of w_k Re(u^H f) per CTA
   int herm_n;              // > 0: the fastest axis is the half spectrum of a real field of this length
@@ -176,6 +176,33 @@ A0_HD int swz(int n) {
   return W == 4 ? (n ^ ((n >> 3) & 1)) : n;
 }
 
+// Row index swz(nb + m*STRIDE) written so that, with m a compile-time constant, it is ONE of two
+// per-item base values plus an immediate: the swizzle only toggles bit 0 with bit 3, and the
+// strides that occur for W = 4 are multiples of 16 (bit 3 of nb decides), 8 (bit 3 alternates
+// with m) and 1 with nb a multiple of 8 (bit 0 of m is toggled by bit 3 of nb).
+template <int W, int STRIDE>
+A0_HD int row_of(int nb, int m) {
+  if constexpr (W != 4) {
+    return nb + m * STRIDE;
+  } else if constexpr (STRIDE % 16 == 0) {
+    return (nb ^ ((nb >> 3) & 1)) + m * STRIDE;
+  } else if constexpr (STRIDE == 8) {
+    return (nb ^ (((nb >> 3) ^ m) & 1)) + m * STRIDE;
+  } else {
+    static_assert(STRIDE == 1, "unexpected stride for W = 4");
+    const int b = (nb >> 3) & 1;  // nb is a multiple of 8
+    return (m & 1) ? nb - b + m : nb + b + m;
+  }
+}
+
+A0_HD void prefetch_l2(const void *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // Configuration: N0 = R0*R1*R2 (R2 = 1: two stages), W columns per tile.
 template <int N0_, int W_, int R0_, int R1_, int R2_>
 struct Cfg {
@@ -186,68 +213,104 @@ struct Cfg {
   static constexpr int THREADS = 256;
   static constexpr int MINB = (N0_ * W_ * 3 * 16 + N0_ * 16) <= 110 * 1024 ? 2 : 1;
   static constexpr size_t smem_bytes(int dim) { return size_t(N0_) * 16 + size_t(dim) * N0_ * W_ * 16; }
+  // twiddle table (device array of N0 complex, staged in shared memory): stage 0 at [0], entry
+  // (m-1)*stride0 + j = w_N0^(j m); stage 1 (three-stage plans) behind it, entry (m-1)*stride1 + j =
+  // w_{N0/R0}^(j m).  Consecutive lanes (consecutive j) read consecutive words: no bank conflicts.
+  static constexpr int TW1 = (R0_ - 1) * (N0_ / R0_);
   static_assert(R0_ * R1_ * R2_ == N0_, "radices must multiply to N0");
   static_assert(RL == 8, "the stride-1 stage must be radix 8 (bank swizzle)");
   static_assert(W_ % 4 == 0 && THREADS % W_ == 0, "W must divide the CTA size");
 };
 
 // ---- forward stage (not the last one): radix R on sub-blocks of size BS -----------------
+// tws: this stage's twiddle table ([m-1][j], see Cfg).  FIRST: inputs come from global memory; the
+// loads of component c+1 are issued before the butterflies of component c (register double
+// buffer), so that the global latency of one component hides behind the arithmetic of another.
 template <class C, int DIM, int R, int BS, bool FIRST>
-A0_HD void fwd_stage(int tid, double2 *data, const double2 *tw, const Params &p, long long col0) {
-  constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R, twstep = N0 / BS;
+A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p, long long col0) {
+  constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R;
   for (int item = tid; item < nbf * W; item += C::THREADS) {
     const int w = item % W, q = item / W;
     if (col0 + w >= p.S) continue;
     const int blk = q / stride, j = q % stride;
     const int nb = blk * BS + j;
-#pragma unroll 1
-    for (int c = 0; c < DIM; c++) {
-      double2 a[R];
+    double2 t[R - 1];
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const int n = nb + r * stride;
-        a[r] = FIRST ? ld_stream(p.X + c * p.comp_stride + (long long)n * p.S + col0 + w)
-                     : data[(c * N0 + swz<W>(n)) * W + w];
+    for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
+    const double2 *g = p.X + (long long)nb * p.S + col0 + w;
+    double2 nxt[R];
+    if constexpr (FIRST) {
+#pragma unroll
+      for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.S);
+    }
+    double2 *d = data + w;
+#pragma unroll 1
+    for (int c = 0; c < DIM; c++, d += N0 * W) {
+      double2 a[R];
+      if constexpr (FIRST) {
+#pragma unroll
+        for (int r = 0; r < R; r++) a[r] = nxt[r];
+        if (c + 1 < DIM) {
+          g += p.comp_stride;
+#pragma unroll
+          for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.S);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) a[r] = d[row_of<W, stride>(nb, r) * W];
       }
       Dft<R, false>::run(a);
 #pragma unroll
-      for (int m = 1; m < R; m++) {
-        const double2 t = tw[j * m * twstep];
-        a[m] = cmul(a[m], t.x, t.y);
-      }
+      for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, t[m - 1].y);
 #pragma unroll
-      for (int m = 0; m < R; m++) data[(c * N0 + swz<W>(nb + m * stride)) * W + w] = a[m];
+      for (int m = 0; m < R; m++) d[row_of<W, stride>(nb, m) * W] = a[m];
     }
   }
 }
 
 // ---- inverse stage (not the first one): transposed forward stage, conjugated twiddles --------
 template <class C, int DIM, int R, int BS, bool LAST>
-A0_HD void inv_stage(int tid, double2 *data, const double2 *tw, const Params &p, long long col0) {
-  constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R, twstep = N0 / BS;
+A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p, long long col0) {
+  constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R;
   for (int item = tid; item < nbf * W; item += C::THREADS) {
     const int w = item % W, q = item / W;
     if (col0 + w >= p.S) continue;
     const int blk = q / stride, j = q % stride;
     const int nb = blk * BS + j;
+    double2 t[R - 1];
+#pragma unroll
+    for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
+    double2 *g = p.X + (long long)nb * p.S + col0 + w;
+    const double2 *d = data + w;
 #pragma unroll 1
-    for (int c = 0; c < DIM; c++) {
+    for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride) {
       double2 a[R];
 #pragma unroll
-      for (int m = 0; m < R; m++) a[m] = data[(c * N0 + swz<W>(nb + m * stride)) * W + w];
+      for (int m = 0; m < R; m++) a[m] = d[row_of<W, stride>(nb, m) * W];
 #pragma unroll
-      for (int m = 1; m < R; m++) {
-        const double2 t = tw[j * m * twstep];
-        a[m] = cmul(a[m], t.x, -t.y);
-      }
+      for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, -t[m - 1].y);
       Dft<R, true>::run(a);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const int n = nb + r * stride;
-        if (LAST) st_stream(p.X + c * p.comp_stride + (long long)n * p.S + col0 + w, a[r]);
-        else data[(c * N0 + swz<W>(n)) * W + w] = a[r];
+        if (LAST) st_stream(g + (long long)r * stride * p.S, a[r]);
+        else const_cast<double2 *>(d)[row_of<W, stride>(nb, r) * W] = a[r];
       }
     }
+  }
+}
+
+// L2 prefetch of the NEXT tile of this CTA (issued while the current tile is being transformed):
+// the first stage's global loads then hit L2 instead of waiting for HBM.  One lane per 64-byte
+// row segment (W = 4) or per 128 bytes (wider tiles).
+template <class C, int DIM>
+A0_HD void prefetch_tile(int tid, const Params &p, long long col0) {
+  constexpr int SEG = C::W >= 8 ? C::W / 8 : 1;  // 128-byte pieces per row
+  if (col0 >= p.S) return;
+  for (int i = tid; i < C::N0 * SEG * DIM; i += C::THREADS) {
+    const int c = i / (C::N0 * SEG), rem = i % (C::N0 * SEG);
+    const int n = rem / SEG, sgm = rem % SEG;
+    const long long col = col0 + sgm * 8;
+    if (col < p.S) prefetch_l2(p.X + c * p.comp_stride + (long long)n * p.S + col);
   }
 }
 
@@ -290,15 +353,21 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
     const long long col = col0 + w;
     if (col >= p.S) continue;
     const int nb = q * R;
+    double2 *d = data + w;
+    // last forward stage (no twiddle after it); the LAST component stays in registers
+    double2 last[R];
 #pragma unroll 1
-    for (int c = 0; c < DIM; c++) {  // last forward stage: no twiddle after it
+    for (int c = 0; c < DIM - 1; c++) {
       double2 a[R];
 #pragma unroll
-      for (int r = 0; r < R; r++) a[r] = data[(c * N0 + swz<W>(nb + r)) * W + w];
+      for (int r = 0; r < R; r++) a[r] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
       Dft<R, false>::run(a);
 #pragma unroll
-      for (int r = 0; r < R; r++) data[(c * N0 + swz<W>(nb + r)) * W + w] = a[r];
+      for (int r = 0; r < R; r++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = a[r];
     }
+#pragma unroll
+    for (int r = 0; r < R; r++) last[r] = d[((DIM - 1) * N0 + row_of<W, 1>(nb, r)) * W];
+    Dft<R, false>::run(last);
     // position nb + r holds frequency k0 = kbase + r * (N0 / R): digits of q, least significant
     // stage first (decimation in frequency leaves the spectrum in digit-reversed order)
     int kbase;
@@ -317,51 +386,62 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
       k_last = k1;
     }
     const double wgt = (p.herm_n > 0 && k_last != 0 && 2 * k_last != p.herm_n) ? 2. : 1.;
-#pragma unroll 2
+#pragma unroll
     for (int r = 0; r < R; r++) {
       const int k0 = kbase + r * nbf;
       phi[0] = ld_tab(p.tab0 + k0); chi[0] = ld_tab(p.tab0 + N0 + k0); psi[0] = ld_tab(p.tab0 + 2 * N0 + k0);
       double2 u[DIM], f[DIM];
 #pragma unroll
-      for (int c = 0; c < DIM; c++) u[c] = data[(c * N0 + swz<W>(nb + r)) * W + w];
+      for (int c = 0; c < DIM - 1; c++) u[c] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
+      u[DIM - 1] = last[r];
       stiffness_times<DIM>(phi, chi, psi, p.mu, p.scaling, u, f);
 #pragma unroll
-      for (int c = 0; c < DIM; c++) {
-        f[c].x *= p.out_scale; f[c].y *= p.out_scale;
-        data[(c * N0 + swz<W>(nb + r)) * W + w] = f[c];
-      }
-      if (p.dot_partial) {
-        double d = u[0].x * f[0].x + u[0].y * f[0].y;
+      for (int c = 0; c < DIM; c++) { f[c].x *= p.out_scale; f[c].y *= p.out_scale; }
 #pragma unroll
-        for (int c = 1; c < DIM; c++) d += u[c].x * f[c].x + u[c].y * f[c].y;
-        dot_acc += wgt * d;
+      for (int c = 0; c < DIM - 1; c++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = f[c];
+      last[r] = f[DIM - 1];
+      if (p.dot_partial) {
+        double dd = u[0].x * f[0].x + u[0].y * f[0].y;
+#pragma unroll
+        for (int c = 1; c < DIM; c++) dd += u[c].x * f[c].x + u[c].y * f[c].y;
+        dot_acc += wgt * dd;
       }
     }
+    // first inverse stage (stride 1, no twiddle before it): the register-resident component first
+    Dft<R, true>::run(last);
+#pragma unroll
+    for (int r = 0; r < R; r++) d[((DIM - 1) * N0 + row_of<W, 1>(nb, r)) * W] = last[r];
 #pragma unroll 1
-    for (int c = 0; c < DIM; c++) {  // first inverse stage (stride 1): no twiddle before it
+    for (int c = 0; c < DIM - 1; c++) {
       double2 a[R];
 #pragma unroll
-      for (int r = 0; r < R; r++) a[r] = data[(c * N0 + swz<W>(nb + r)) * W + w];
+      for (int r = 0; r < R; r++) a[r] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
       Dft<R, true>::run(a);
 #pragma unroll
-      for (int r = 0; r < R; r++) data[(c * N0 + swz<W>(nb + r)) * W + w] = a[r];
+      for (int r = 0; r < R; r++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = a[r];
     }
   }
 }
 
-// Phase PH of a tile for thread `tid`; a CTA barrier separates consecutive phases.
+// Phase PH of a tile for thread `tid`; a CTA barrier separates consecutive phases.  next_col0: first
+// column of the tile this CTA processes next (prefetched into L2 during phase 1).
 template <class C, int DIM, int PH>
-A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, double &dot_acc) {
+A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, long long next_col0,
+                 double &dot_acc) {
   if constexpr (C::NS == 3) {
     if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
-    else if constexpr (PH == 1) fwd_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw, p, col0);
-    else if constexpr (PH == 2) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
-    else if constexpr (PH == 3) inv_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw, p, col0);
+    else if constexpr (PH == 1) {
+      prefetch_tile<C, DIM>(tid, p, next_col0);
+      fwd_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
+    } else if constexpr (PH == 2) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
+    else if constexpr (PH == 3) inv_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
     else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
   } else {
     if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
-    else if constexpr (PH == 1) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
-    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+    else if constexpr (PH == 1) {
+      prefetch_tile<C, DIM>(tid, p, next_col0);
+      mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
+    } else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
   }
 }
 
@@ -372,12 +452,13 @@ void emulate_host(const Params &p, double *dot_out) {
   double *acc = new double[C::THREADS]();
   for (long long tile = 0; tile < p.n_tiles; tile++) {
     const long long col0 = tile * C::W;
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, acc[t]);
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, acc[t]);
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, acc[t]);
+    const long long nx = col0 + C::W;
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, nx, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, nx, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, nx, acc[t]);
     if constexpr (C::NPH > 3) {
-      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, acc[t]);
-      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, nx, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, nx, acc[t]);
     }
   }
   if (dot_out) {

@@ -388,6 +388,25 @@ class ModalOperator {
   void freq_index_map(std::int32_t *k_out_dev, void *stream = nullptr) const {
     check(bri17_freq_index_map(plan_, k_out_dev, nullptr, nullptr, stream));
   }
+  // Per-mode direct solves over the whole grid, planar fields (Hooke::modal_eigenstress_to_opposite_strain
+  // batched, reference :308-355): u^ = K^-1 f^; f^ = tau^ . conj(B^) (:340); u^ = K^-1 f^ of that (:341);
+  // eta^ = sym(B^ (x) u^) (:342-353).
+  void solve_modal_stiffness(const complex_t *f_hat_dev, complex_t *u_hat_dev, void *stream = nullptr) const {
+    check(bri17_modal_stiffness_solve_f64(plan_, f_hat_dev, u_hat_dev, nullptr, nullptr, 0, 0, stream));
+  }
+  void eigenstress_to_force(const complex_t *tau_hat_dev, complex_t *f_hat_dev, void *stream = nullptr) const {
+    check(bri17_eigenstress_to_force_f64(plan_, tau_hat_dev, f_hat_dev, nullptr, nullptr, 0, 0, 0, 0, stream));
+  }
+  void eigenstress_to_displacement(const complex_t *tau_hat_dev, complex_t *u_hat_dev,
+                                   void *stream = nullptr) const {
+    check(bri17_eigenstress_to_displacement_f64(plan_, tau_hat_dev, u_hat_dev, nullptr, nullptr, 0, 0, 0, 0,
+                                                stream));
+  }
+  void eigenstress_to_opposite_strain(const complex_t *tau_hat_dev, complex_t *eta_hat_dev,
+                                      void *stream = nullptr) const {
+    check(bri17_eigenstress_to_opposite_strain_f64(plan_, tau_hat_dev, eta_hat_dev, nullptr, nullptr, 0, 0,
+                                                   stream));
+  }
 
   bri17_plan *c_plan() const { return plan_; }
 
@@ -437,7 +456,19 @@ class RealSpaceOperator {
   void apply(const double *u_dev, double *F_dev, void *stream = nullptr) const {
     check(bri17_real_space_apply_real_f64(plan_, u_dev, F_dev, stream));
   }
-  // Conjugate gradients on A x = b (zero-mean b); returns the iteration count.
+  // F = A u and the global scalar <u, A u> (Parseval sum taken inside the K^ kernel).
+  double apply_with_dot(const complex_t *u_dev, complex_t *F_dev, void *stream = nullptr) const {
+    double dot = 0.;
+    check(bri17_real_space_apply_dot_f64(plan_, u_dev, F_dev, 0, &dot, stream));
+    return dot;
+  }
+  double apply_with_dot(const double *u_dev, double *F_dev, void *stream = nullptr) const {
+    double dot = 0.;
+    check(bri17_real_space_apply_dot_f64(plan_, u_dev, F_dev, 1, &dot, stream));
+    return dot;
+  }
+  // Conjugate gradients on A x = b (the component means of b are projected out: K^(0) = 0,
+  // reference :336-339); returns the iteration count.
   int solve(const complex_t *b_dev, complex_t *x_dev, double rtol = 1e-8, int max_iter = 1000,
             double *rel_residual = nullptr, void *stream = nullptr) const {
     int it = 0;
