@@ -73,7 +73,7 @@ RS_SIGNATURES = {
     "bri17_real_space_apply_dot_f64": (C.c_int, [_vp, _vp, _vp, C.c_int, _f64p, _vp]),
     "bri17_debug_axis0_fused_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                                _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
-                                               C.c_int, _vp, _f64p]),
+                                               C.c_int, C.c_int, _vp, _f64p]),
 }
 
 _lib = None

@@ -21,17 +21,17 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) axis0_fused_kernel(const 
   __syncthreads();
   double dot = 0.;
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const long long col0 = tile * C::W, nx = (tile + gridDim.x) * C::W;
-    phase<C, DIM, 0>(tid, data, tw, p, col0, nx, dot);
+    const long long col0 = tile * C::W;
+    phase<C, DIM, 0>(tid, data, tw, p, col0, dot);
     __syncthreads();
-    phase<C, DIM, 1>(tid, data, tw, p, col0, nx, dot);
+    phase<C, DIM, 1>(tid, data, tw, p, col0, dot);
     __syncthreads();
-    phase<C, DIM, 2>(tid, data, tw, p, col0, nx, dot);
+    phase<C, DIM, 2>(tid, data, tw, p, col0, dot);
     __syncthreads();
     if constexpr (C::NPH > 3) {
-      phase<C, DIM, 3>(tid, data, tw, p, col0, nx, dot);
+      phase<C, DIM, 3>(tid, data, tw, p, col0, dot);
       __syncthreads();
-      phase<C, DIM, 4>(tid, data, tw, p, col0, nx, dot);
+      phase<C, DIM, 4>(tid, data, tw, p, col0, dot);
       __syncthreads();
     }
   }

@@ -26,6 +26,14 @@
 // n ^ ((n >> 3) & 1), which puts the two rows in different halves of the 128 B line and leaves the
 // other stages' quarter-warps contiguous.
 //
+// Global layout.  A tile reads N0 row segments of W*16 bytes per component.  With the natural layout
+// [c][n0][k1][k2] the rows of a column are n1*S2e*16 bytes apart (4 MiB at 512^3): every row is another
+// 2 MB page and another DRAM page, and a pure copy with this pattern reaches 2.3 TB/s on B200
+// (tests/cpp/seg_bw.cu: 64-byte segments, 4 MiB stride) -- the first version of this kernel ran at that
+// limit.  The k1-major layout [c][k1][n0][k2] puts the rows S2e*16 bytes apart (8 KiB): 5.0 TB/s for
+// the same copy.  The producers write it for free: the exchange kernel stores every received row at
+// (k1, n0) instead of (n0, k1); on one GPU cuFFT's advanced output layout does.
+//
 // Everything below the kernel is __host__ __device__: tests replay the phases thread by thread on
 // the CPU (bri17_debug_axis0_fused_host) against numpy's FFT, so that index arithmetic is checked
 // without a GPU.
@@ -45,9 +53,14 @@ namespace bri17b200 {
 namespace axis0 {
 
 struct Params {
-  double2 *X;              // [dim][N0][S], transformed in place
+  double2 *X;              // dim components of N0 x S complex, transformed in place; element (c, n0,
+                           // column j) at c*comp_stride + (j / blk_cols)*blk_stride + j % blk_cols + n0*row_stride
   long long comp_stride;   // complex elements between components (>= N0*S)
-  long long S;             // columns (complex elements per n0 row)
+  long long row_stride;    // ... between consecutive n0 of one column
+  long long blk_stride;    // ... between consecutive blocks of blk_cols columns
+  long long blk_cols;      // natural layout [n0][S]: blk_cols = S, row_stride = S;
+                           // k1-major layout [k1][n0][S2e]: blk_cols = S2e, row_stride = S2e, blk_stride = N0*S2e
+  long long S;             // columns
   long long n_tiles;       // ceil(S / W)
   int N0;
   int S2e;                 // 3-D: extent of the fastest axis in the block (column = b*S2e + k2); 2-D: 1
@@ -195,12 +208,10 @@ A0_HD int row_of(int nb, int m) {
   }
 }
 
-A0_HD void prefetch_l2(const void *p) {
-#ifdef __CUDA_ARCH__
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
+// Offset of column j (row n0 = 0) inside a component.
+A0_HD long long col_base(const Params &p, long long j) {
+  const long long b = j / p.blk_cols;
+  return b * p.blk_stride + (j - b * p.blk_cols);
 }
 
 // Configuration: N0 = R0*R1*R2 (R2 = 1: two stages), W columns per tile.
@@ -237,11 +248,11 @@ A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p
     double2 t[R - 1];
 #pragma unroll
     for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
-    const double2 *g = p.X + (long long)nb * p.S + col0 + w;
+    const double2 *g = p.X + col_base(p, col0 + w) + (long long)nb * p.row_stride;
     double2 nxt[R];
     if constexpr (FIRST) {
 #pragma unroll
-      for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.S);
+      for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.row_stride);
     }
     double2 *d = data + w;
 #pragma unroll 1
@@ -253,7 +264,7 @@ A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p
         if (c + 1 < DIM) {
           g += p.comp_stride;
 #pragma unroll
-          for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.S);
+          for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.row_stride);
         }
       } else {
 #pragma unroll
@@ -280,7 +291,7 @@ A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p
     double2 t[R - 1];
 #pragma unroll
     for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
-    double2 *g = p.X + (long long)nb * p.S + col0 + w;
+    double2 *g = p.X + col_base(p, col0 + w) + (long long)nb * p.row_stride;
     const double2 *d = data + w;
 #pragma unroll 1
     for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride) {
@@ -292,25 +303,10 @@ A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p
       Dft<R, true>::run(a);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        if (LAST) st_stream(g + (long long)r * stride * p.S, a[r]);
+        if (LAST) st_stream(g + (long long)r * stride * p.row_stride, a[r]);
         else const_cast<double2 *>(d)[row_of<W, stride>(nb, r) * W] = a[r];
       }
     }
-  }
-}
-
-// L2 prefetch of the NEXT tile of this CTA (issued while the current tile is being transformed):
-// the first stage's global loads then hit L2 instead of waiting for HBM.  One lane per 64-byte
-// row segment (W = 4) or per 128 bytes (wider tiles).
-template <class C, int DIM>
-A0_HD void prefetch_tile(int tid, const Params &p, long long col0) {
-  constexpr int SEG = C::W >= 8 ? C::W / 8 : 1;  // 128-byte pieces per row
-  if (col0 >= p.S) return;
-  for (int i = tid; i < C::N0 * SEG * DIM; i += C::THREADS) {
-    const int c = i / (C::N0 * SEG), rem = i % (C::N0 * SEG);
-    const int n = rem / SEG, sgm = rem % SEG;
-    const long long col = col0 + sgm * 8;
-    if (col < p.S) prefetch_l2(p.X + c * p.comp_stride + (long long)n * p.S + col);
   }
 }
 
@@ -423,25 +419,21 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
   }
 }
 
-// Phase PH of a tile for thread `tid`; a CTA barrier separates consecutive phases.  next_col0: first
-// column of the tile this CTA processes next (prefetched into L2 during phase 1).
+// Phase PH of a tile for thread `tid`; a CTA barrier separates consecutive phases.
+// (An L2 prefetch of the CTA's next tile was tried here and removed: it raised the DRAM reads of a
+// 512^3 pass from 6.4 to 11.3 GB without shortening the load phase -- profiles/r02_axis0_fused.md.)
 template <class C, int DIM, int PH>
-A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, long long next_col0,
-                 double &dot_acc) {
+A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, double &dot_acc) {
   if constexpr (C::NS == 3) {
     if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
-    else if constexpr (PH == 1) {
-      prefetch_tile<C, DIM>(tid, p, next_col0);
-      fwd_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
-    } else if constexpr (PH == 2) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
+    else if constexpr (PH == 1) fwd_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
+    else if constexpr (PH == 2) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
     else if constexpr (PH == 3) inv_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
     else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
   } else {
     if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
-    else if constexpr (PH == 1) {
-      prefetch_tile<C, DIM>(tid, p, next_col0);
-      mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
-    } else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+    else if constexpr (PH == 1) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
+    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
   }
 }
 
@@ -452,13 +444,12 @@ void emulate_host(const Params &p, double *dot_out) {
   double *acc = new double[C::THREADS]();
   for (long long tile = 0; tile < p.n_tiles; tile++) {
     const long long col0 = tile * C::W;
-    const long long nx = col0 + C::W;
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, nx, acc[t]);
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, nx, acc[t]);
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, nx, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, acc[t]);
+    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, acc[t]);
     if constexpr (C::NPH > 3) {
-      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, nx, acc[t]);
-      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, nx, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, acc[t]);
     }
   }
   if (dot_out) {

@@ -76,14 +76,19 @@ namespace {
 
 constexpr int MAX_RANKS = 16;
 
-// One family of equal-length row pieces to move: for c < ncomp, a < rows:
-//   dst[c*dst_cs + a*dst_rs + (0..len)] = scale * src[c*src_cs + a*src_rs + (0..len)]
+// One family of equal-length row pieces to move: for c < ncomp, a < rows, e < len:
+//   dst[c*dst_cs + a*dst_rs + off(e, dst_bs)] = scale * src[c*src_cs + a*src_rs + off(e, src_bs)]
+// off(e, bs) = (e / inner)*bs + e % inner: a piece is len/inner runs of `inner` contiguous elements,
+// `bs` apart (bs = inner: the piece is contiguous).  The k1-major Fourier-side layout
+// [c][k1][n0][k2] makes the (c, n0) piece of a rank a set of k1 runs N0*S2e apart.
 struct CopySeg {
   const double2 *src;
   double2 *dst;
   long long src_cs, src_rs, dst_cs, dst_rs;
+  long long src_bs, dst_bs;
   int rows;
   int len;
+  int inner;
 };
 struct CopyPlan {
   CopySeg seg[MAX_RANKS];
@@ -119,19 +124,46 @@ __global__ void __launch_bounds__(256) slab_copy_kernel(const CopyPlan cp, int f
   double2 *dst = g.dst + c * g.dst_cs + a * g.dst_rs;
   const bool scaled = cp.scale != 1.0;
   int i = begin + threadIdx.x;
-  for (; i + 3 * 256 < end; i += 4 * 256) {
-    double2 v0 = __ldcs(src + i), v1 = __ldcs(src + i + 256), v2 = __ldcs(src + i + 512),
-            v3 = __ldcs(src + i + 768);
-    if (scaled) {
-      v0.x *= cp.scale; v0.y *= cp.scale; v1.x *= cp.scale; v1.y *= cp.scale;
-      v2.x *= cp.scale; v2.y *= cp.scale; v3.x *= cp.scale; v3.y *= cp.scale;
+  if (g.src_bs == g.inner && g.dst_bs == g.inner) {  // contiguous on both sides
+    for (; i + 3 * 256 < end; i += 4 * 256) {
+      double2 v0 = __ldcs(src + i), v1 = __ldcs(src + i + 256), v2 = __ldcs(src + i + 512),
+              v3 = __ldcs(src + i + 768);
+      if (scaled) {
+        v0.x *= cp.scale; v0.y *= cp.scale; v1.x *= cp.scale; v1.y *= cp.scale;
+        v2.x *= cp.scale; v2.y *= cp.scale; v3.x *= cp.scale; v3.y *= cp.scale;
+      }
+      dst[i] = v0; dst[i + 256] = v1; dst[i + 512] = v2; dst[i + 768] = v3;
     }
-    dst[i] = v0; dst[i + 256] = v1; dst[i + 512] = v2; dst[i + 768] = v3;
-  }
-  for (; i < end; i += 256) {
-    double2 v = __ldcs(src + i);
-    if (scaled) { v.x *= cp.scale; v.y *= cp.scale; }
-    dst[i] = v;
+    for (; i < end; i += 256) {
+      double2 v = __ldcs(src + i);
+      if (scaled) { v.x *= cp.scale; v.y *= cp.scale; }
+      dst[i] = v;
+    }
+  } else {  // runs of `inner` elements, src_bs / dst_bs apart
+    const unsigned inner = unsigned(g.inner);
+    for (; i + 3 * 256 < end; i += 4 * 256) {
+      long long so[4], dd[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned e = unsigned(i + j * 256), b = e / inner, k = e - b * inner;
+        so[j] = b * g.src_bs + k;
+        dd[j] = b * g.dst_bs + k;
+      }
+      double2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = __ldcs(src + so[j]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (scaled) { v[j].x *= cp.scale; v[j].y *= cp.scale; }
+        dst[dd[j]] = v[j];
+      }
+    }
+    for (; i < end; i += 256) {
+      const unsigned e = unsigned(i), b = e / inner, k = e - b * inner;
+      double2 v = __ldcs(src + b * g.src_bs + k);
+      if (scaled) { v.x *= cp.scale; v.y *= cp.scale; }
+      dst[b * g.dst_bs + k] = v;
+    }
   }
  }
   if (fence_system) __threadfence_system();
@@ -365,6 +397,10 @@ struct Layout {
   int64_t fourier_count = 0;  // ... of the Fourier-side block [N0][n1_loc][S2e]
   cufftHandle fwd_local = 0, inv_local = 0, axis0 = 0;
   bool have_local = false, have_axis0 = false;
+  // single GPU, 3-D, fused axis-0 pass: the same local transforms writing / reading the k1-major
+  // layout [k1][n0][S2e] through cuFFT's advanced data layout (created on first use)
+  cufftHandle fwd_local_t = 0, inv_local_t = 0;
+  bool have_local_t = false;
 };
 
 struct bri17_rs_plan {
@@ -394,6 +430,7 @@ struct bri17_rs_plan {
   unsigned long long epoch_bar[2] = {0, 0}, epoch_red = 0;
   // fused axis-0 pass (axis0_fused.cuh): own device copies of phi|chi|psi per axis + twiddles
   int fused = 1;               // option "fused_axis0"; used when axis0::supported(shape[0])
+  int xt = 1;                  // option "k1_major": k1-major Fourier-side layout with the fused pass (3-D)
   double *tabs = nullptr;      // [axis][3][N_axis]
   int64_t tab_off[3] = {0, 0, 0};
   double2 *twiddle = nullptr;
@@ -465,7 +502,7 @@ int scalar_allreduce(bri17_rs_plan *p, double *v, int n, cudaStream_t st) {
 // c0/ncomp select components of the multi-component arrays T and X; `barriers` = false leaves
 // the cross-GPU synchronisation to the caller (pipelined apply).
 int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double2 *X, double2 *S, int ncomp,
-                     cudaStream_t st, int c0 = 0, bool barriers = true) {
+                     cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   CopyPlan cp{};
   cp.ncomp = ncomp;
@@ -484,9 +521,17 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
     g.src = T + (long long)l.k1_beg[q] * S2e + c0 * g.src_cs;
     g.rows = p->n0_loc;
     g.len = n1q * S2e;
+    g.inner = S2e;
+    g.src_bs = g.dst_bs = S2e;
     maxlen = std::max(maxlen, g.len);
     const bool direct = (q == r) || p->mode == 1;  // store at the final position
-    if (direct) {
+    if (direct && xt) {  // k1-major Fourier-side layout X[c][b][n0][k2]
+      double2 *base = (q == r) ? X : p->peerW[q];
+      g.dst_cs = (long long)N0 * n1q * S2e;
+      g.dst_rs = S2e;
+      g.dst_bs = (long long)N0 * S2e;
+      g.dst = base + (long long)p->n0_beg[r] * S2e + c0 * g.dst_cs;
+    } else if (direct) {
       double2 *base = (q == r) ? X : p->peerW[q];
       g.dst_cs = (long long)N0 * n1q * S2e;
       g.dst_rs = (long long)n1q * S2e;
@@ -521,7 +566,7 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
 // Backward exchange: Fourier-side X[c][n0][b_loc][k2] -> local-transform layout D[c][a][b][k2] (times scale).
 // mode 0: R = packed receive buffer, D written by the unpack; mode 1: peers store into our W2 (= D).
 int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, double2 *D, double2 *R, int ncomp,
-                      double scale, cudaStream_t st, int c0 = 0, bool barriers = true) {
+                      double scale, cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   if (p->mode == 1 || P == 1) {
     // every row (c, n0) goes, whole, to the owner of n0, at its final position
@@ -533,9 +578,17 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
       const int n0q = p->n0_beg[q + 1] - p->n0_beg[q];
       if (n0q == 0 || l.n1_loc == 0) continue;
       CopySeg &g = cp.seg[cp.nseg++];
+      g.inner = S2e;
+      g.src_bs = g.dst_bs = S2e;
       g.src_cs = (long long)N0 * l.n1_loc * S2e;
-      g.src_rs = (long long)l.n1_loc * S2e;
-      g.src = X + (long long)p->n0_beg[q] * l.n1_loc * S2e + c0 * g.src_cs;
+      if (xt) {  // k1-major source X[c][b][n0][k2]
+        g.src_rs = S2e;
+        g.src_bs = (long long)N0 * S2e;
+        g.src = X + (long long)p->n0_beg[q] * S2e + c0 * g.src_cs;
+      } else {
+        g.src_rs = (long long)l.n1_loc * S2e;
+        g.src = X + (long long)p->n0_beg[q] * l.n1_loc * S2e + c0 * g.src_cs;
+      }
       g.rows = n0q;
       g.len = l.n1_loc * S2e;
       double2 *base = (q == r) ? D : p->peerW2[q];
@@ -574,6 +627,8 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
     CopySeg &g = cp.seg[cp.nseg++];
     g.rows = p->n0_loc;
     g.len = n1q * S2e;
+    g.inner = S2e;
+    g.src_bs = g.dst_bs = S2e;
     maxlen = std::max(maxlen, g.len);
     if (q == r) {  // own block straight from X
       g.src = X + (long long)p->n0_beg[r] * n1q * S2e;
@@ -684,6 +739,10 @@ void destroy_layout(Layout &l) {
     if (l.real) cufftDestroy(l.inv_local);
   }
   if (l.have_axis0) cufftDestroy(l.axis0);
+  if (l.have_local_t) {
+    cufftDestroy(l.fwd_local_t);
+    cufftDestroy(l.inv_local_t);
+  }
   l = Layout{};
 }
 
@@ -702,13 +761,42 @@ int ensure_buffers(bri17_rs_plan *p, size_t bytes) {
 // Is the fused axis-0 pass used for this plan?
 bool use_fused(const bri17_rs_plan *p) { return p->fused && p->tabs && bri17b200::axis0::supported(p->shape[0]); }
 
+// Is the Fourier-side block kept k1-major, [c][k1][n0][k2] (axis0_fused.cuh, "Global layout")?
+// 3-D only, with the fused pass, when the producer can write it: the fused exchange kernel (mode 1)
+// or, on one GPU, cuFFT's advanced output layout.
+bool use_xt(const bri17_rs_plan *p) {
+  return p->xt && p->dim == 3 && use_fused(p) && (p->nranks == 1 || p->mode == 1);
+}
+
+// Single GPU: local transforms over axes (1, 2) whose spectral side is k1-major:
+// element (k1, k2) of plane n0 at k1*(N0*S2e) + n0*S2e + k2.
+int setup_layout_t(bri17_rs_plan *p, Layout &l) {
+  if (l.have_local_t || p->n0_loc == 0) return BRI17_OK;
+  size_t ws = 0;
+  long long n64[2] = {p->shape[1], p->N2e};
+  const long long rplane = (long long)p->shape[1] * p->N2e;
+  long long nat[2] = {p->shape[1], p->N2e};                               // natural real-space planes
+  long long spec[2] = {l.S1, (long long)p->shape[0] * l.S2e};            // k1 stride = N0*S2e
+  RS_CUFFT_TRY(cufftCreate(&l.fwd_local_t));
+  RS_CUFFT_TRY(cufftCreate(&l.inv_local_t));
+  if (!l.real) {
+    RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local_t, 2, n64, nat, 1, rplane, spec, 1, l.S2e, CUFFT_Z2Z, p->n0_loc, &ws));
+    RS_CUFFT_TRY(cufftMakePlanMany64(l.inv_local_t, 2, n64, spec, 1, l.S2e, nat, 1, rplane, CUFFT_Z2Z, p->n0_loc, &ws));
+  } else {
+    RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local_t, 2, n64, nat, 1, rplane, spec, 1, l.S2e, CUFFT_D2Z, p->n0_loc, &ws));
+    RS_CUFFT_TRY(cufftMakePlanMany64(l.inv_local_t, 2, n64, spec, 1, l.S2e, nat, 1, rplane, CUFFT_Z2D, p->n0_loc, &ws));
+  }
+  l.have_local_t = true;
+  return BRI17_OK;
+}
+
 // Axis-0 section of the apply on the Fourier-side block X of a layout, in place:
 //   FFT(axis 0) -> K^ . (.) * |h|/|N| -> unnormalised inverse FFT(axis 0)
 // (tests/test_bri17.cpp:57 [axis 0], :58-92, :93-106, :95 [axis 0]).  One kernel when N0 is a
 // supported power of two, cuFFT + modal kernel + cuFFT otherwise.  dot_dev (optional, device
 // scalar) receives sum_k w_k Re(u^_k^H f^_k) over THIS rank's block (= its share of <u, A u>).
 // Events 3 and 4 bracket the modal kernel (or the whole fused pass).
-int modal_section(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st, double *dot_dev) {
+int modal_section(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st, double *dot_dev, bool xt) {
   const int dim = p->dim;
   const int herm_n = l.real ? p->shape[dim - 1] : 0;
   if (dot_dev && !p->dot_scratch) BRI17_CUDA_TRY(cudaMalloc(&p->dot_scratch, sizeof(double) * RED_CTAS));
@@ -725,6 +813,15 @@ int modal_section(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st
     a.X = X;
     a.comp_stride = l.fourier_count;
     a.S = (long long)l.n1_loc * l.S2e;
+    if (xt) {  // [k1][n0][k2]
+      a.row_stride = l.S2e;
+      a.blk_cols = l.S2e;
+      a.blk_stride = (long long)p->shape[0] * l.S2e;
+    } else {   // [n0][k1][k2]
+      a.row_stride = a.S;
+      a.blk_cols = std::max<long long>(a.S, 1);
+      a.blk_stride = 0;
+    }
     a.N0 = p->shape[0];
     a.S2e = dim == 3 ? l.S2e : 1;
     a.k1_begin = l.k1_beg[p->rank];
@@ -747,6 +844,7 @@ int modal_section(bri17_rs_plan *p, const Layout &l, double2 *X, cudaStream_t st
     mark(p, 5, st);
     return BRI17_OK;
   }
+  if (xt) return fail(BRI17_ERR_UNSUPPORTED, "k1-major layout without the fused axis-0 pass");
   RS_TRY(fft_axis0(p, l, X, dim, CUFFT_FORWARD, st));                       // :57 (axis 0)
   mark(p, 3, st);
   int kb[3] = {0, l.k1_beg[p->rank], 0};
@@ -851,13 +949,14 @@ int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFw
                     cudaStream_t st, double *dot_dev) {
   const int dim = p->dim;
   double2 *X = p->W;
+  const bool xt = use_xt(p);
   p->timings_valid = false;
   mark(p, 0, st);
   for (int c = 0; c < dim; c++) {
     RS_TRY(local_fwd(c));
     BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
     BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
-    RS_TRY(exchange_forward(p, l, T, X, nullptr, 1, p->sx, c, false));
+    RS_TRY(exchange_forward(p, l, T, X, nullptr, 1, p->sx, c, false, xt));
     RS_TRY(exchange_barrier(p));
     BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
   }
@@ -867,11 +966,11 @@ int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFw
   if (fused || dot_dev) {
     // the axis-0 section needs every component: wait for the three forward exchanges
     for (int c = 0; c < dim; c++) BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
-    RS_TRY(modal_section(p, l, X, st, dot_dev));
+    RS_TRY(modal_section(p, l, X, st, dot_dev, xt));
     for (int c = 0; c < dim; c++) {
       if (c == 0) BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[0], st));
       BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[0], 0));
-      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false, xt));
       RS_TRY(exchange_barrier(p));
       BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
     }
@@ -1179,29 +1278,57 @@ int check_fields(const bri17_rs_plan *p, const void *a, const void *b) {
 }
 
 int apply_complex(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st, double *dot_dev) {
-  const Layout &l = p->lc;
+  Layout &l = p->lc;
   const double2 *u = static_cast<const double2 *>(u_dev);
   double2 *F = static_cast<double2 *>(F_dev);
   const int dim = p->dim;
+  const bool xt = use_xt(p);
   if (p->nranks > 1 && p->mode == 1 && p->pipeline) {
     auto fwd = [&](int c) { return fft_local_c2c(p, u + c * l.t_count, F + c * l.t_count, 1, CUFFT_FORWARD, st); };
     auto inv = [&](int c) { return fft_local_c2c(p, p->W2 + c * l.t_count, F + c * l.t_count, 1, CUFFT_INVERSE, st); };
     return apply_pipelined(p, l, F, fwd, inv, st, dot_dev);
   }
   p->timings_valid = false;
+  if (p->nranks == 1 && xt) {
+    // one GPU, k1-major spectral layout: u -> (cuFFT, transposed output) W2 -> fused pass in place
+    // -> (cuFFT, transposed input) F
+    RS_TRY(setup_layout_t(p, l));
+    RS_TRY(ensure_buffers(p, std::max<size_t>(sizeof(double2) * dim * l.t_count, 16)));
+    double2 *X = p->W2;
+    mark(p, 0, st);
+    if (l.have_local_t) {
+      RS_CUFFT_TRY(cufftSetStream(l.fwd_local_t, st));
+      for (int c = 0; c < dim; c++)
+        RS_CUFFT_TRY(cufftExecZ2Z(l.fwd_local_t, (cufftDoubleComplex *)(u + c * l.t_count),
+                                  (cufftDoubleComplex *)(X + c * l.t_count), CUFFT_FORWARD));
+    }
+    mark(p, 1, st);
+    mark(p, 2, st);
+    RS_TRY(modal_section(p, l, X, st, dot_dev, true));
+    mark(p, 6, st);
+    if (l.have_local_t) {
+      RS_CUFFT_TRY(cufftSetStream(l.inv_local_t, st));
+      for (int c = 0; c < dim; c++)
+        RS_CUFFT_TRY(cufftExecZ2Z(l.inv_local_t, (cufftDoubleComplex *)(X + c * l.t_count),
+                                  (cufftDoubleComplex *)(F + c * l.t_count), CUFFT_INVERSE));
+    }
+    mark(p, 7, st);
+    p->timings_valid = true;
+    return BRI17_OK;
+  }
   mark(p, 0, st);
   RS_TRY(fft_local_c2c(p, u, F, dim, CUFFT_FORWARD, st));                   // :57 (axes 1..)
   mark(p, 1, st);
   double2 *X = F;  // Fourier-side block
   if (p->nranks > 1) {
     X = p->W;
-    RS_TRY(exchange_forward(p, l, F, p->W, p->W2, dim, st));
+    RS_TRY(exchange_forward(p, l, F, p->W, p->W2, dim, st, 0, true, xt));
   }
   mark(p, 2, st);
-  RS_TRY(modal_section(p, l, X, st, dot_dev));                              // :57 (axis 0), :58-106, :95 (axis 0)
+  RS_TRY(modal_section(p, l, X, st, dot_dev, xt));                          // :57 (axis 0), :58-106, :95 (axis 0)
   if (p->nranks > 1) {
     if (p->mode == 1) {
-      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st, 0, true, xt));
       mark(p, 6, st);
       RS_TRY(fft_local_c2c(p, p->W2, F, dim, CUFFT_INVERSE, st));
     } else {
@@ -1227,28 +1354,33 @@ int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st
   if (p->nranks == 1) RS_TRY(ensure_buffers(p, std::max<size_t>(sizeof(double2) * dim * l.t_count, 16)));
   const double *u = static_cast<const double *>(u_dev);
   double *F = static_cast<double *>(F_dev);
-  double2 *T = p->W2;  // local-transform layout [c][n0_loc][S1][S2e]
+  double2 *T = p->W2;  // local-transform layout [c][n0_loc][S1][S2e] ([c][S1][n0][S2e] when k1-major on one GPU)
+  const bool xt = use_xt(p);
+  const bool local_t = xt && p->nranks == 1;
+  if (local_t) RS_TRY(setup_layout_t(p, l));
   // cuFFT wants 16-byte aligned real arrays; component c starts at c*real_count doubles, which
   // is misaligned when the slab holds an odd number of values: stage those through rbuf.
   if ((p->real_count & 1) && !p->rbuf) BRI17_CUDA_TRY(cudaMalloc(&p->rbuf, sizeof(double) * (p->real_count + 2)));
   auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; };
   auto local_fwd = [&](int c) -> int {  // D2Z u_c -> T_c
     if (!l.have_local) return BRI17_OK;
-    RS_CUFFT_TRY(cufftSetStream(l.fwd_local, st));
+    const cufftHandle plan = local_t ? l.fwd_local_t : l.fwd_local;
+    RS_CUFFT_TRY(cufftSetStream(plan, st));
     double *src = const_cast<double *>(u) + c * p->real_count;
     if (misaligned(src)) {
       BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
       src = p->rbuf;
     }
-    RS_CUFFT_TRY(cufftExecD2Z(l.fwd_local, src, (cufftDoubleComplex *)(T + c * l.t_count)));
+    RS_CUFFT_TRY(cufftExecD2Z(plan, src, (cufftDoubleComplex *)(T + c * l.t_count)));
     return BRI17_OK;
   };
   auto local_inv = [&](int c) -> int {  // Z2D (W2)_c -> F_c
     if (!l.have_local) return BRI17_OK;
-    RS_CUFFT_TRY(cufftSetStream(l.inv_local, st));
+    const cufftHandle plan = local_t ? l.inv_local_t : l.inv_local;
+    RS_CUFFT_TRY(cufftSetStream(plan, st));
     double *dst = F + c * p->real_count;
     double *out = misaligned(dst) ? p->rbuf : dst;
-    RS_CUFFT_TRY(cufftExecZ2D(l.inv_local, (cufftDoubleComplex *)(p->W2 + c * l.t_count), out));
+    RS_CUFFT_TRY(cufftExecZ2D(plan, (cufftDoubleComplex *)(p->W2 + c * l.t_count), out));
     if (out != dst)
       BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
     return BRI17_OK;
@@ -1263,13 +1395,13 @@ int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st
   if (p->nranks > 1) {
     X = p->W;
     double2 *S = p->W2 + p->real_upper;  // packed send pieces (NCCL mode)
-    RS_TRY(exchange_forward(p, l, T, p->W, S, dim, st));
+    RS_TRY(exchange_forward(p, l, T, p->W, S, dim, st, 0, true, xt));
   }
   mark(p, 2, st);
-  RS_TRY(modal_section(p, l, X, st, dot_dev));
+  RS_TRY(modal_section(p, l, X, st, dot_dev, xt));
   if (p->nranks > 1) {
     if (p->mode == 1) {
-      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st));   // peers store into our W2
+      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, dim, 1.0, st, 0, true, xt));   // peers store into our W2
     } else {
       double2 *R = p->W2 + p->real_upper;                                 // packed receive pieces
       RS_TRY(exchange_backward(p, l, X, p->W2, R, dim, 1.0, st));
@@ -1305,6 +1437,7 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
   if (!p || !key) return fail(BRI17_ERR_INVALID_ARG, "plan/key is NULL");
   if (!std::strcmp(key, "pipeline")) p->pipeline = value != 0;
   else if (!std::strcmp(key, "fused_axis0")) p->fused = value != 0;
+  else if (!std::strcmp(key, "k1_major")) p->xt = value != 0;
   else if (!std::strcmp(key, "copy_ctas")) {
     if (value < 1) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 1");
     p->copy_ctas = int(value);
@@ -1315,6 +1448,7 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
 int bri17_rs_plan_get_info(const bri17_rs_plan *p, const char *key, int64_t *value) {
   if (!p || !key || !value) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
   if (!std::strcmp(key, "fused_axis0")) *value = use_fused(p) ? 1 : 0;
+  else if (!std::strcmp(key, "k1_major")) *value = use_xt(p) ? 1 : 0;
   else if (!std::strcmp(key, "fused_launches")) *value = p->fused_launches;
   else if (!std::strcmp(key, "pipeline")) *value = (p->nranks > 1 && p->mode == 1 && p->pipeline) ? 1 : 0;
   else if (!std::strcmp(key, "exchange_mode")) *value = p->mode;
@@ -1383,7 +1517,8 @@ int bri17_real_space_apply_dot_f64(bri17_rs_plan *p, const void *u_dev, void *F_
 // the CPU.  X: [dim][N0][S] complex, in place.  tabs: phi|chi|psi of axis d at tabs_d ([3][N_d]).
 int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, int k1_begin, int N1, int N2,
                                  const double *tab0, const double *tab1, const double *tab2, double mu,
-                                 double nu, double out_scale, int hermitian_n, void *X_host, double *dot_out) {
+                                 double nu, double out_scale, int hermitian_n, int k1_major, void *X_host,
+                                 double *dot_out) {
   if (!X_host || !tab0 || !tab1 || (dim == 3 && !tab2)) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
   if (dim != 2 && dim != 3) return fail(BRI17_ERR_INVALID_ARG, "dim must be 2 or 3");
   if (!bri17b200::axis0::supported(N0)) return fail(BRI17_ERR_UNSUPPORTED, "unsupported N0");
@@ -1393,6 +1528,15 @@ int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, int k1_beg
   a.X = static_cast<double2 *>(X_host);
   a.comp_stride = int64_t(N0) * S;
   a.S = S;
+  if (k1_major && dim == 3) {
+    a.row_stride = S2e;
+    a.blk_cols = S2e;
+    a.blk_stride = int64_t(N0) * S2e;
+  } else {
+    a.row_stride = S;
+    a.blk_cols = std::max<int64_t>(S, 1);
+    a.blk_stride = 0;
+  }
   a.N0 = N0;
   a.S2e = dim == 3 ? S2e : 1;
   a.k1_begin = k1_begin;

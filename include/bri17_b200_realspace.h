@@ -62,7 +62,9 @@ BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
  * transforms of the others on a second stream; default 1, fused exchange only),
  * "copy_ctas" (grid cap of the exchange kernel), "fused_axis0" (1 = run FFT(axis 0) ->
  * K^ -> inverse FFT(axis 0) as one kernel when shape[0] is 16..1024 and a power of two;
- * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths). */
+ * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths),
+ * "k1_major" (1 = with the fused pass in 3-D, keep the Fourier-side block as [c][k1][n0][k2]
+ * so that the rows a tile gathers are S2e*16 bytes apart instead of n1*S2e*16; default 1). */
 BRI17_API int bri17_rs_plan_set_option(bri17_rs_plan *plan, const char *key, int64_t value);
 /* "fused_axis0" (is the fused pass in use), "fused_launches", "pipeline", "exchange_mode",
  * "barriers" (flag barriers issued so far). */
@@ -153,11 +155,13 @@ BRI17_API int bri17_cg_solve_real_f64(bri17_rs_plan *plan, const void *b_dev, vo
  * (FFT(axis 0) -> K^ * out_scale -> inverse FFT(axis 0)) thread by thread on the CPU,
  * in place on X_host[dim][N0][S] (complex128).  Column j is (k1, k2) = (k1_begin +
  * j / S2e, j % S2e) in 3-D, k1 = k1_begin + j in 2-D.  tab_d: phi|chi|psi of axis d
- * ([3][N_d], bri17_plan_get_tables).  dot_out (optional): sum_k w_k Re(u^H f). */
+ * ([3][N_d], bri17_plan_get_tables).  k1_major (3-D): X_host is [dim][S/S2e][N0][S2e] instead of
+ * [dim][N0][S] (the layout the operator keeps its Fourier-side block in, see
+ * bri17_rs_plan_set_option "k1_major").  dot_out (optional): sum_k w_k Re(u^H f). */
 BRI17_API int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, int k1_begin, int N1,
                                            int N2, const double *tab0, const double *tab1,
                                            const double *tab2, double mu, double nu, double out_scale,
-                                           int hermitian_n, void *X_host, double *dot_out);
+                                           int hermitian_n, int k1_major, void *X_host, double *dot_out);
 
 #ifdef __cplusplus
 }

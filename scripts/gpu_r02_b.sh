@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 TAG=${1:-b}
 timeout 900 python -m pytest tests/test_gpu_realspace.py -m gpu -x -q > gpurun_out/r02_${TAG}_pytest_rs.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r02_${TAG}_pytest_rs.log
-for extra in "" "--real" "--edge 1024 --applies 2"; do
+for extra in "" "--real" "--no-k1-major" "--no-k1-major --real" "--no-fused"; do
   timeout 300 python scripts/run_realspace.py --edge 512 --applies 10 --cg 10 $extra 2>&1 | grep "^{" | tee -a gpurun_out/r02_${TAG}_realspace_n1.jsonl
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:axis0_fused -s 2 -c 1 \

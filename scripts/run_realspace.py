@@ -18,6 +18,7 @@ ap.add_argument("--edge", type=int, default=512)
 ap.add_argument("--applies", type=int, default=3)
 ap.add_argument("--real", action="store_true")
 ap.add_argument("--no-fused", action="store_true")
+ap.add_argument("--no-k1-major", action="store_true")
 ap.add_argument("--cg", type=int, default=0, help="also time this many CG iterations")
 args = ap.parse_args()
 
@@ -26,6 +27,8 @@ L = tuple(n * h for n, h in zip(shape, (1.1, 1.2, 1.3)))
 op = RealSpaceOperator(shape, L, 5.6, 0.3)
 if args.no_fused:
     op.set_option("fused_axis0", 0)
+if args.no_k1_major:
+    op.set_option("k1_major", 0)
 if args.real:
     u = torch.randn(op.real_shape, dtype=torch.float64, device="cuda")
     fn = op.apply_real
@@ -43,6 +46,7 @@ for _ in range(args.applies):
 e1.record()
 torch.cuda.synchronize()
 out = {"edge": args.edge, "real": args.real, "fused_axis0": bool(op.info("fused_axis0")),
+       "k1_major": bool(op.info("k1_major")),
        "ms_per_apply": e0.elapsed_time(e1) / args.applies, "phases_ms": op.timings()}
 if args.cg:
     b = fn(u).clone()

@@ -86,7 +86,8 @@ def main():
         if rank == 0:
             print(f"{name}: {fmt.format(value)} (bound {bound:g}) {'ok' if good else 'FAIL'}", flush=True)
 
-    configs = ((1, 1, 1), (1, 0, 1), (0, 0, 1), (1, 1, 0))       # (exchange mode, pipeline, fused axis 0)
+    # (exchange mode, pipeline, axis-0 path: 1 fused + k1-major layout, 2 fused + natural layout, 0 cuFFT)
+    configs = ((1, 1, 1), (1, 0, 1), (0, 0, 1), (1, 1, 0), (1, 1, 2))
     for mode, pipeline, fused in configs[:2] if quick else configs:
         tag = f"mode {mode} pipeline {pipeline} fused {fused}"
         report(f"{tag}: small grids vs numpy restatement", rc.small_grids(local, mode, pipeline, fused), 1e-13)

@@ -46,12 +46,15 @@ def _max_over_ranks(value, device):
 
 
 def _make(shape, L, mu, nu, local_rank, mode, pipeline=None, fused=None):
+    """fused: 1 = fused axis-0 pass on the k1-major layout (default), 2 = fused pass on the natural
+    layout, 0 = cuFFT + modal kernel + cuFFT."""
     from bri17_b200.realspace import RealSpaceOperator
     op = RealSpaceOperator.from_process_group(shape, L, mu, nu, device=local_rank, exchange_mode=mode)
     if pipeline is not None:
         op.set_option("pipeline", pipeline)
     if fused is not None:
-        op.set_option("fused_axis0", fused)
+        op.set_option("fused_axis0", 1 if fused else 0)
+        op.set_option("k1_major", 1 if fused == 1 else 0)
     return op
 
 

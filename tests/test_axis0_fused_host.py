@@ -28,7 +28,7 @@ def _tables(shape, L):
     return out
 
 
-def _run(shape, L, k1_begin, n1_loc, S2e, X, out_scale=1.0, herm=0, want_dot=False):
+def _run(shape, L, k1_begin, n1_loc, S2e, X, out_scale=1.0, herm=0, want_dot=False, k1_major=0):
     """X: (dim, N0, n1_loc[, S2e]) complex128 block of a grid `shape` whose fastest spectral
     extent is S2e (3-D) -- in place through the CPU replay."""
     lib = _lib.load_rs()
@@ -39,7 +39,7 @@ def _run(shape, L, k1_begin, n1_loc, S2e, X, out_scale=1.0, herm=0, want_dot=Fal
     dot = C.c_double(0.0)
     rc = lib.bri17_debug_axis0_fused_host(dim, shape[0], S, S2e if dim == 3 else 1, k1_begin, shape[1],
                                           shape[2] if dim == 3 else 1, p[0], p[1], p[2], MU, NU,
-                                          out_scale, herm, X.ctypes.data,
+                                          out_scale, herm, k1_major, X.ctypes.data,
                                           C.byref(dot) if want_dot else None)
     assert rc == 0, _lib.load().bri17_last_error()
     return dot.value
@@ -117,11 +117,30 @@ def test_fused_axis0_dot_full_spectrum(oracle_mod):
     assert abs(dot - float(np.sum(np.real(np.conj(X) * got)))) <= 1e-12 * abs(expect)
 
 
+@pytest.mark.parametrize("N0", [32, 512, 1024])
+def test_fused_axis0_k1_major_layout(oracle_mod, N0):
+    """The k1-major global layout [c][k1][n0][k2] (rows of a column S2e elements apart) gives the
+    same result as the natural layout [c][n0][k1][k2]; tiles straddle k1 blocks (S2e = 7)."""
+    shape = (N0, 9, 12)
+    L = (1.1 * N0, 10.8, 15.6)
+    S2e, k1_begin, n1_loc = 7, 3, 5
+    rng = np.random.default_rng(N0 + 1)
+    X = rng.standard_normal((3, N0, n1_loc, S2e)) + 1j * rng.standard_normal((3, N0, n1_loc, S2e))
+    _, _, ref = _reference(oracle_mod, shape, L, k1_begin, X, 0.5)
+    Xt = np.ascontiguousarray(X.transpose(0, 2, 1, 3))                 # [c][k1][n0][k2]
+    dot = _run(shape, L, k1_begin, n1_loc, S2e, Xt, out_scale=0.5, herm=12, want_dot=True, k1_major=1)
+    got = Xt.transpose(0, 2, 1, 3)
+    assert np.abs(got - ref).max() <= 2e-14 * np.abs(ref).max()
+    nat = X.copy()
+    dot_nat = _run(shape, L, k1_begin, n1_loc, S2e, nat, out_scale=0.5, herm=12, want_dot=True)
+    assert np.array_equal(nat, got) and dot == dot_nat
+
+
 def test_fused_axis0_unsupported_length():
     lib = _lib.load_rs()
     X = np.zeros((3, 48, 4), dtype=np.complex128)
     t = np.zeros(3 * 48)
     tp = t.ctypes.data_as(C.POINTER(C.c_double))
-    rc = lib.bri17_debug_axis0_fused_host(3, 48, 4, 2, 0, 48, 48, tp, tp, tp, 1.0, 0.3, 1.0, 0,
+    rc = lib.bri17_debug_axis0_fused_host(3, 48, 4, 2, 0, 48, 48, tp, tp, tp, 1.0, 0.3, 1.0, 0, 0,
                                           X.ctypes.data, None)
     assert rc == _lib.ERR_UNSUPPORTED

@@ -159,16 +159,21 @@ def test_fused_axis0_pass_equals_cufft_path(oracle_mod, shape):
     uc, ur = torch.from_numpy(u + 0j).cuda(), torch.from_numpy(u).cuda()
     Fc, Fr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
     assert op.info("fused_launches") == 2
+    assert op.info("k1_major") == (dim == 3)             # k1-major spectral layout (3-D, fused pass)
+    op.set_option("k1_major", 0)                           # fused pass on the natural layout
+    Hc, Hr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
+    assert op.info("fused_launches") == 4 and op.info("k1_major") == 0
     op.set_option("fused_axis0", 0)
     assert op.info("fused_axis0") == 0
     Gc, Gr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
-    assert op.info("fused_launches") == 2
+    assert op.info("fused_launches") == 4
     scale = np.abs(ref).max()
-    for got in (Fc, Gc):
+    for got in (Fc, Gc, Hc):
         assert np.abs(got - ref).max() <= 1e-13 * scale
-    for got in (Fr, Gr):
+    for got in (Fr, Gr, Hr):
         assert np.abs(got - ref.real).max() <= 1e-13 * scale
     assert np.abs(Fc - Gc).max() <= 1e-13 * scale and np.abs(Fr - Gr).max() <= 1e-13 * scale
+    assert torch.equal(uc.cpu(), torch.from_numpy(u + 0j)) and torch.equal(ur.cpu(), torch.from_numpy(u))
 
 
 @pytest.mark.parametrize("shape", [(16, 12, 10), (9, 6, 7), (64, 33), (12, 10)])
