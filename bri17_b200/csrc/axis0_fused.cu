@@ -20,20 +20,22 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) axis0_fused_kernel(const 
   for (int i = tid; i < C::N0; i += C::THREADS) tw[i] = p.twiddle[i];
   __syncthreads();
   double dot = 0.;
+  if (blockIdx.x < p.n_tiles) issue_tile_loads<C, DIM>(tid, data, p, (long long)blockIdx.x * C::W);
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const long long col0 = tile * C::W;
-    phase<C, DIM, 0>(tid, data, tw, p, col0, dot);
+    const long long nx = tile + gridDim.x < p.n_tiles ? (tile + gridDim.x) * C::W : -1;
+    phase<C, DIM, 0>(tid, data, tw, p, col0, nx, dot);  // waits for this thread's async copies
     __syncthreads();
-    phase<C, DIM, 1>(tid, data, tw, p, col0, dot);
+    phase<C, DIM, 1>(tid, data, tw, p, col0, nx, dot);
     __syncthreads();
-    phase<C, DIM, 2>(tid, data, tw, p, col0, dot);
-    __syncthreads();
+    phase<C, DIM, 2>(tid, data, tw, p, col0, nx, dot);
     if constexpr (C::NPH > 3) {
-      phase<C, DIM, 3>(tid, data, tw, p, col0, dot);
       __syncthreads();
-      phase<C, DIM, 4>(tid, data, tw, p, col0, dot);
+      phase<C, DIM, 3>(tid, data, tw, p, col0, nx, dot);
       __syncthreads();
+      phase<C, DIM, 4>(tid, data, tw, p, col0, nx, dot);
     }
+    // no barrier here: the next tile's first stage works on the slots this thread just used
   }
   if (p.dot_partial) {  // deterministic CTA sum -> one partial per CTA
     __shared__ double sh[C::THREADS / 32];

@@ -208,6 +208,22 @@ A0_HD int row_of(int nb, int m) {
   }
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register is held while the data is in
+// flight.  Host replay: an ordinary copy.
+A0_HD void cp_async16(double2 *smem_dst, const double2 *gsrc) {
+#ifdef __CUDA_ARCH__
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+  *smem_dst = *gsrc;
+#endif
+}
+A0_HD void cp_async_wait_all() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // Offset of column j (row n0 = 0) inside a component.
 A0_HD long long col_base(const Params &p, long long j) {
   const long long b = j / p.blk_cols;
@@ -233,13 +249,34 @@ struct Cfg {
   static_assert(W_ % 4 == 0 && THREADS % W_ == 0, "W must divide the CTA size");
 };
 
+// ---- loads of a tile: every thread copies the inputs of ITS first-stage butterflies, all
+// components, asynchronously into the shared-memory slots those butterflies work in.  The same
+// thread owns the same slots in the last inverse stage, so the copies for the NEXT tile are issued
+// there, slot by slot as soon as the current tile's value has been read (inv_stage<LAST>): the global
+// latency hides behind that stage instead of being exposed after a barrier.
+template <class C, int DIM>
+A0_HD void issue_tile_loads(int tid, double2 *data, const Params &p, long long col0) {
+  constexpr int N0 = C::N0, W = C::W, R = C::R0, stride = N0 / R, nbf = N0 / R;
+  for (int item = tid; item < nbf * W; item += C::THREADS) {
+    const int w = item % W, nb = item / W;  // first stage: one block, j = q
+    if (col0 + w >= p.S) continue;
+    const double2 *g = p.X + col_base(p, col0 + w) + (long long)nb * p.row_stride;
+    double2 *d = data + w;
+    for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride) {
+#pragma unroll
+      for (int r = 0; r < R; r++) cp_async16(d + row_of<W, stride>(nb, r) * W, g + (long long)r * stride * p.row_stride);
+    }
+  }
+}
+
 // ---- forward stage (not the last one): radix R on sub-blocks of size BS -----------------
-// tws: this stage's twiddle table ([m-1][j], see Cfg).  FIRST: inputs come from global memory; the
-// loads of component c+1 are issued before the butterflies of component c (register double
-// buffer), so that the global latency of one component hides behind the arithmetic of another.
+// tws: this stage's twiddle table ([m-1][j], see Cfg).  FIRST: the inputs were copied into this
+// thread's own slots by issue_tile_loads / the previous tile's last stage; wait for them (no CTA
+// barrier is needed: nobody else touches these slots before the barrier that ends this stage).
 template <class C, int DIM, int R, int BS, bool FIRST>
 A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p, long long col0) {
   constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R;
+  if constexpr (FIRST) cp_async_wait_all();
   for (int item = tid; item < nbf * W; item += C::THREADS) {
     const int w = item % W, q = item / W;
     if (col0 + w >= p.S) continue;
@@ -248,28 +285,12 @@ A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p
     double2 t[R - 1];
 #pragma unroll
     for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
-    const double2 *g = p.X + col_base(p, col0 + w) + (long long)nb * p.row_stride;
-    double2 nxt[R];
-    if constexpr (FIRST) {
-#pragma unroll
-      for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.row_stride);
-    }
     double2 *d = data + w;
 #pragma unroll 1
     for (int c = 0; c < DIM; c++, d += N0 * W) {
       double2 a[R];
-      if constexpr (FIRST) {
 #pragma unroll
-        for (int r = 0; r < R; r++) a[r] = nxt[r];
-        if (c + 1 < DIM) {
-          g += p.comp_stride;
-#pragma unroll
-          for (int r = 0; r < R; r++) nxt[r] = ld_stream(g + (long long)r * stride * p.row_stride);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; r++) a[r] = d[row_of<W, stride>(nb, r) * W];
-      }
+      for (int r = 0; r < R; r++) a[r] = d[row_of<W, stride>(nb, r) * W];
       Dft<R, false>::run(a);
 #pragma unroll
       for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, t[m - 1].y);
@@ -280,31 +301,45 @@ A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p
 }
 
 // ---- inverse stage (not the first one): transposed forward stage, conjugated twiddles --------
+// LAST: results go straight to global memory (natural order), and the freed slots are refilled
+// with the next tile's inputs (next_col0; < 0 or >= S: nothing to prefetch).
 template <class C, int DIM, int R, int BS, bool LAST>
-A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p, long long col0) {
+A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p, long long col0,
+                     long long next_col0 = -1) {
   constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R;
   for (int item = tid; item < nbf * W; item += C::THREADS) {
     const int w = item % W, q = item / W;
-    if (col0 + w >= p.S) continue;
+    const bool have = col0 + w < p.S;
+    const bool more = LAST && next_col0 >= 0 && next_col0 + w < p.S;
+    if (!have && !more) continue;
     const int blk = q / stride, j = q % stride;
     const int nb = blk * BS + j;
     double2 t[R - 1];
 #pragma unroll
     for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
-    double2 *g = p.X + col_base(p, col0 + w) + (long long)nb * p.row_stride;
-    const double2 *d = data + w;
+    double2 *g = p.X + (have ? col_base(p, col0 + w) : 0) + (long long)nb * p.row_stride;
+    const double2 *gn = p.X + (more ? col_base(p, next_col0 + w) : 0) + (long long)nb * p.row_stride;
+    double2 *d = data + w;
 #pragma unroll 1
-    for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride) {
+    for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride, gn += p.comp_stride) {
       double2 a[R];
 #pragma unroll
-      for (int m = 0; m < R; m++) a[m] = d[row_of<W, stride>(nb, m) * W];
+      for (int m = 0; m < R; m++) a[m] = have ? d[row_of<W, stride>(nb, m) * W] : make_double2(0., 0.);
+      if constexpr (LAST) {
+        if (more) {
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            cp_async16(d + row_of<W, stride>(nb, r) * W, gn + (long long)r * stride * p.row_stride);
+        }
+      }
+      if (!have) continue;
 #pragma unroll
       for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, -t[m - 1].y);
       Dft<R, true>::run(a);
 #pragma unroll
       for (int r = 0; r < R; r++) {
         if (LAST) st_stream(g + (long long)r * stride * p.row_stride, a[r]);
-        else const_cast<double2 *>(d)[row_of<W, stride>(nb, r) * W] = a[r];
+        else d[row_of<W, stride>(nb, r) * W] = a[r];
       }
     }
   }
@@ -419,21 +454,25 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
   }
 }
 
-// Phase PH of a tile for thread `tid`; a CTA barrier separates consecutive phases.
-// (An L2 prefetch of the CTA's next tile was tried here and removed: it raised the DRAM reads of a
+// Phase PH of a tile for thread `tid`.  A CTA barrier separates consecutive phases of a tile; none is
+// needed between the last phase of a tile and the first phase of the next (same slot ownership).
+// next_col0: first column of the tile this CTA processes next (its inputs are prefetched by the last
+// phase), -1 if none.
+// (An L2 prefetch instruction per row was tried instead and removed: it raised the DRAM reads of a
 // 512^3 pass from 6.4 to 11.3 GB without shortening the load phase -- profiles/r02_axis0_fused.md.)
 template <class C, int DIM, int PH>
-A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, double &dot_acc) {
+A0_HD void phase(int tid, double2 *data, const double2 *tw, const Params &p, long long col0, long long next_col0,
+                 double &dot_acc) {
   if constexpr (C::NS == 3) {
     if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
     else if constexpr (PH == 1) fwd_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
     else if constexpr (PH == 2) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
     else if constexpr (PH == 3) inv_stage<C, DIM, C::R1, C::N0 / C::R0, false>(tid, data, tw + C::TW1, p, col0);
-    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0, next_col0);
   } else {
     if constexpr (PH == 0) fwd_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
     else if constexpr (PH == 1) mid_phase<C, DIM>(tid, data, p, col0, dot_acc);
-    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0);
+    else inv_stage<C, DIM, C::R0, C::N0, true>(tid, data, tw, p, col0, next_col0);
   }
 }
 
@@ -442,14 +481,23 @@ template <class C, int DIM>
 void emulate_host(const Params &p, double *dot_out) {
   double2 *data = new double2[size_t(DIM) * C::N0 * C::W];
   double *acc = new double[C::THREADS]();
-  for (long long tile = 0; tile < p.n_tiles; tile++) {
-    const long long col0 = tile * C::W;
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, acc[t]);
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, acc[t]);
-    for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, acc[t]);
-    if constexpr (C::NPH > 3) {
-      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, acc[t]);
-      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, acc[t]);
+  // same schedule as the kernel with a grid of 3 CTAs replayed one after the other, so that the
+  // "next tile" prefetch and the missing barrier between tiles are exercised
+  const long long G = 3;
+  for (long long cta = 0; cta < G; cta++) {
+    if (cta < p.n_tiles)
+      for (int t = 0; t < C::THREADS; t++) issue_tile_loads<C, DIM>(t, data, p, cta * C::W);
+    for (long long tile = cta; tile < p.n_tiles; tile += G) {
+      const long long col0 = tile * C::W, nx = tile + G < p.n_tiles ? (tile + G) * C::W : -1;
+      // no barrier between the last phase of a tile and phase 0 of the next: replay them fused per
+      // thread where the kernel would run them back to back -- here phase 0 follows in program order
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 0>(t, data, p.twiddle, p, col0, nx, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 1>(t, data, p.twiddle, p, col0, nx, acc[t]);
+      for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 2>(t, data, p.twiddle, p, col0, nx, acc[t]);
+      if constexpr (C::NPH > 3) {
+        for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 3>(t, data, p.twiddle, p, col0, nx, acc[t]);
+        for (int t = 0; t < C::THREADS; t++) phase<C, DIM, 4>(t, data, p.twiddle, p, col0, nx, acc[t]);
+      }
     }
   }
   if (dot_out) {
