@@ -430,7 +430,7 @@ struct bri17_rs_plan {
   unsigned long long epoch_bar[2] = {0, 0}, epoch_red = 0;
   // fused axis-0 pass (axis0_fused.cuh): own device copies of phi|chi|psi per axis + twiddles
   int fused = 1;               // option "fused_axis0"; used when axis0::supported(shape[0])
-  int xt = 1;                  // option "k1_major": k1-major Fourier-side layout with the fused pass (3-D)
+  int xt = -1;                 // option "k1_major": k1-major Fourier-side layout with the fused pass (3-D); -1 auto
   double *tabs = nullptr;      // [axis][3][N_axis]
   int64_t tab_off[3] = {0, 0, 0};
   double2 *twiddle = nullptr;
@@ -764,8 +764,14 @@ bool use_fused(const bri17_rs_plan *p) { return p->fused && p->tabs && bri17b200
 // Is the Fourier-side block kept k1-major, [c][k1][n0][k2] (axis0_fused.cuh, "Global layout")?
 // 3-D only, with the fused pass, when the producer can write it: the fused exchange kernel (mode 1)
 // or, on one GPU, cuFFT's advanced output layout.
-bool use_xt(const bri17_rs_plan *p) {
-  return p->xt && p->dim == 3 && use_fused(p) && (p->nranks == 1 || p->mode == 1);
+// Option "k1_major": 1 always, 0 never, -1 (default) where it pays: always with the fused exchange
+// (free); on one GPU only for complex fields -- cuFFT's transposed output costs 0.8 ms per 512^3
+// apply, the fused pass gains 1.8 ms on complex fields (12.96 vs 14.06 ms per apply) but only 0.56 ms
+// on the half spectrum (8.53 vs 8.24 ms), profiles/r02_measurements.md.
+bool use_xt(const bri17_rs_plan *p, const Layout &l) {
+  if (p->xt == 0 || p->dim != 3 || !use_fused(p) || !(p->nranks == 1 || p->mode == 1)) return false;
+  if (p->xt > 0 || p->nranks > 1) return true;
+  return !l.real;
 }
 
 // Single GPU: local transforms over axes (1, 2) whose spectral side is k1-major:
@@ -949,7 +955,7 @@ int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFw
                     cudaStream_t st, double *dot_dev) {
   const int dim = p->dim;
   double2 *X = p->W;
-  const bool xt = use_xt(p);
+  const bool xt = use_xt(p, l);
   p->timings_valid = false;
   mark(p, 0, st);
   for (int c = 0; c < dim; c++) {
@@ -1282,7 +1288,7 @@ int apply_complex(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t
   const double2 *u = static_cast<const double2 *>(u_dev);
   double2 *F = static_cast<double2 *>(F_dev);
   const int dim = p->dim;
-  const bool xt = use_xt(p);
+  const bool xt = use_xt(p, l);
   if (p->nranks > 1 && p->mode == 1 && p->pipeline) {
     auto fwd = [&](int c) { return fft_local_c2c(p, u + c * l.t_count, F + c * l.t_count, 1, CUFFT_FORWARD, st); };
     auto inv = [&](int c) { return fft_local_c2c(p, p->W2 + c * l.t_count, F + c * l.t_count, 1, CUFFT_INVERSE, st); };
@@ -1355,7 +1361,7 @@ int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st
   const double *u = static_cast<const double *>(u_dev);
   double *F = static_cast<double *>(F_dev);
   double2 *T = p->W2;  // local-transform layout [c][n0_loc][S1][S2e] ([c][S1][n0][S2e] when k1-major on one GPU)
-  const bool xt = use_xt(p);
+  const bool xt = use_xt(p, l);
   const bool local_t = xt && p->nranks == 1;
   if (local_t) RS_TRY(setup_layout_t(p, l));
   // cuFFT wants 16-byte aligned real arrays; component c starts at c*real_count doubles, which
@@ -1437,7 +1443,7 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
   if (!p || !key) return fail(BRI17_ERR_INVALID_ARG, "plan/key is NULL");
   if (!std::strcmp(key, "pipeline")) p->pipeline = value != 0;
   else if (!std::strcmp(key, "fused_axis0")) p->fused = value != 0;
-  else if (!std::strcmp(key, "k1_major")) p->xt = value != 0;
+  else if (!std::strcmp(key, "k1_major")) p->xt = value < 0 ? -1 : (value != 0);
   else if (!std::strcmp(key, "copy_ctas")) {
     if (value < 1) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 1");
     p->copy_ctas = int(value);
@@ -1448,7 +1454,8 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
 int bri17_rs_plan_get_info(const bri17_rs_plan *p, const char *key, int64_t *value) {
   if (!p || !key || !value) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
   if (!std::strcmp(key, "fused_axis0")) *value = use_fused(p) ? 1 : 0;
-  else if (!std::strcmp(key, "k1_major")) *value = use_xt(p) ? 1 : 0;
+  else if (!std::strcmp(key, "k1_major")) *value = use_xt(p, p->lc) ? 1 : 0;
+  else if (!std::strcmp(key, "k1_major_real")) *value = use_xt(p, p->lr) ? 1 : 0;
   else if (!std::strcmp(key, "fused_launches")) *value = p->fused_launches;
   else if (!std::strcmp(key, "pipeline")) *value = (p->nranks > 1 && p->mode == 1 && p->pipeline) ? 1 : 0;
   else if (!std::strcmp(key, "exchange_mode")) *value = p->mode;

@@ -63,11 +63,13 @@ BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
  * "copy_ctas" (grid cap of the exchange kernel), "fused_axis0" (1 = run FFT(axis 0) ->
  * K^ -> inverse FFT(axis 0) as one kernel when shape[0] is 16..1024 and a power of two;
  * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths),
- * "k1_major" (1 = with the fused pass in 3-D, keep the Fourier-side block as [c][k1][n0][k2]
- * so that the rows a tile gathers are S2e*16 bytes apart instead of n1*S2e*16; default 1). */
+ * "k1_major" (with the fused pass in 3-D, keep the Fourier-side block as [c][k1][n0][k2] so that
+ * the rows a tile gathers are S2e*16 bytes apart instead of n1*S2e*16: 1 always, 0 never, -1
+ * (default) whenever the fused exchange writes it, and on one GPU for complex fields only). */
 BRI17_API int bri17_rs_plan_set_option(bri17_rs_plan *plan, const char *key, int64_t value);
-/* "fused_axis0" (is the fused pass in use), "fused_launches", "pipeline", "exchange_mode",
- * "barriers" (flag barriers issued so far). */
+/* "fused_axis0" (is the fused pass in use), "k1_major" / "k1_major_real" (is the k1-major layout
+ * in use for complex / real fields), "fused_launches", "pipeline", "exchange_mode", "barriers"
+ * (flag barriers issued so far). */
 BRI17_API int bri17_rs_plan_get_info(const bri17_rs_plan *plan, const char *key, int64_t *value);
 
 /* Geometry of this rank: real-space slab [n0_begin, n0_begin+n0_count) of axis

@@ -19,6 +19,7 @@ ap.add_argument("--applies", type=int, default=3)
 ap.add_argument("--real", action="store_true")
 ap.add_argument("--no-fused", action="store_true")
 ap.add_argument("--no-k1-major", action="store_true")
+ap.add_argument("--k1-major", action="store_true")
 ap.add_argument("--cg", type=int, default=0, help="also time this many CG iterations")
 args = ap.parse_args()
 
@@ -29,6 +30,8 @@ if args.no_fused:
     op.set_option("fused_axis0", 0)
 if args.no_k1_major:
     op.set_option("k1_major", 0)
+if args.k1_major:
+    op.set_option("k1_major", 1)
 if args.real:
     u = torch.randn(op.real_shape, dtype=torch.float64, device="cuda")
     fn = op.apply_real
@@ -46,7 +49,7 @@ for _ in range(args.applies):
 e1.record()
 torch.cuda.synchronize()
 out = {"edge": args.edge, "real": args.real, "fused_axis0": bool(op.info("fused_axis0")),
-       "k1_major": bool(op.info("k1_major")),
+       "k1_major": bool(op.info("k1_major_real" if args.real else "k1_major")),
        "ms_per_apply": e0.elapsed_time(e1) / args.applies, "phases_ms": op.timings()}
 if args.cg:
     b = fn(u).clone()

@@ -159,10 +159,15 @@ def test_fused_axis0_pass_equals_cufft_path(oracle_mod, shape):
     uc, ur = torch.from_numpy(u + 0j).cuda(), torch.from_numpy(u).cuda()
     Fc, Fr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
     assert op.info("fused_launches") == 2
-    assert op.info("k1_major") == (dim == 3)             # k1-major spectral layout (3-D, fused pass)
+    # default layout policy on one GPU: k1-major for complex fields (3-D), natural for real fields
+    assert op.info("k1_major") == (dim == 3) and op.info("k1_major_real") == 0
     op.set_option("k1_major", 0)                           # fused pass on the natural layout
-    Hc, Hr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
-    assert op.info("fused_launches") == 4 and op.info("k1_major") == 0
+    Hc = op.apply(uc).cpu().numpy()
+    op.set_option("k1_major", 1)                           # ... and forced k1-major for real fields too
+    assert op.info("k1_major_real") == (dim == 3)
+    Hr = op.apply_real(ur).cpu().numpy()
+    assert op.info("fused_launches") == 4
+    op.set_option("k1_major", 0)
     op.set_option("fused_axis0", 0)
     assert op.info("fused_axis0") == 0
     Gc, Gr = op.apply(uc).cpu().numpy(), op.apply_real(ur).cpu().numpy()
