@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--rs-steps", type=int, default=5)
     ap.add_argument("--cg-edge", type=int, default=512)
     ap.add_argument("--cg-max-iter", type=int, default=20000)
+    ap.add_argument("--rs-timeout", type=float, default=900.0,
+                    help="seconds after which the real-space / CG records are abandoned and the headline line is printed")
     return ap.parse_args()
 
 
@@ -313,6 +315,11 @@ def realspace_records(args, torch, dist, local_rank, rank, world, dev):
     except Exception as e:                                  # the headline line must still print
         import traceback
         out["realspace"] = {"error": repr(e), "trace": traceback.format_exc()[-1500:]}
+        try:                                                # a sticky CUDA error: nothing else can run in this process
+            torch.cuda.synchronize()
+        except Exception:
+            out["cg"] = {"error": "skipped: the CUDA context is unusable after the real-space record failed"}
+            return out
 
     # ---- configs[4]: CG on the periodic inclusion problem ----
     try:
@@ -520,10 +527,9 @@ def main():
     f = None
     torch.cuda.empty_cache()
 
-    extra = {"realspace": None, "cg": None}
-    if not args.no_realspace and dim == 3 and edge == 512:
-        extra = realspace_records(args, torch, dist, local_rank, rank, world, dev)
-
+    # ---- the headline line is complete BEFORE the real-space / CG records run: whatever happens in
+    # them (an exception, a poisoned CUDA context, a hang) rank 0 still prints it ----
+    line = None
     if rank == 0:
         traffic = None            # DRAM bytes per launch from the committed ncu --set full capture
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -563,9 +569,36 @@ def main():
                          "timing": "CUDA events on the launch stream around the timed steps / steps, max over ranks"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "weak_scaling": weak,
-            "realspace": extra["realspace"], "cg": extra["cg"],
+            "realspace": None, "cg": None,
         }
-        print(json.dumps(line), flush=True)
+
+    printed = threading.Lock()
+
+    def emit(extra):
+        """Rank 0 prints the line exactly once (other ranks: no-op)."""
+        if rank == 0 and printed.acquire(blocking=False):
+            line.update(extra)
+            print(json.dumps(line), flush=True)
+
+    if not args.no_realspace and dim == 3 and edge == 512:
+        def give_up():                                # the records hang (a peer died, a flag never arrives)
+            emit({"realspace": {"error": f"no result after {args.rs_timeout} s; records abandoned"}, "cg": None})
+            os._exit(0)
+        watchdog = threading.Timer(args.rs_timeout, give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            extra = realspace_records(args, torch, dist, local_rank, rank, world, dev)
+        except BaseException as e:                    # e.g. a sticky CUDA error surfacing outside the records' own handlers
+            extra = {"realspace": {"error": repr(e)}, "cg": None}
+        watchdog.cancel()
+        emit(extra)
+        poisoned = any(isinstance(v, dict) and "error" in v for v in extra.values())
+        if poisoned:                                  # the CUDA context may be unusable: no collective teardown
+            sys.stdout.flush()
+            os._exit(0)
+    else:
+        emit({})
     if world > 1:
         dist.destroy_process_group()
 

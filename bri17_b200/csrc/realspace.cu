@@ -384,6 +384,20 @@ __global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double *x, do
 
 }  // namespace
 
+// Batched transform over the trailing axes of a slab, one plane per batch entry, executed in CHUNKS
+// of consecutive planes.  cuFFT runs a 2-D transform as two kernels (one per axis) with the whole
+// batch between them: over a 512^3 component that is two full passes over HBM.  With a chunk that
+// fits the 126 MB L2 the second kernel finds the first one's output there and overwrites it in
+// place before it is evicted, so the pair costs about ONE read and ONE write of the data
+// (option "fft_chunk_mib"; measured in profiles/r02_measurements.md).
+struct BatchFft {
+  cufftHandle h[2] = {0, 0};        // [0] chunks of `chunk` planes, [1] the remaining `rem` planes
+  int chunk = 0, nfull = 0, rem = 0;
+  long long idist = 0, odist = 0;   // elements of the input / output type between consecutive planes
+  cufftType type = CUFFT_Z2Z;
+  bool made = false;
+};
+
 // Geometry + cuFFT plans of one spectral layout.  "complex": the reference's c2c
 // transforms (tests/test_bri17.cpp:117-127).  "real": r2c/c2r over the trailing
 // axes, only the non-redundant half spectrum of the last axis is kept
@@ -395,11 +409,12 @@ struct Layout {
   int n1_loc = 0;
   int64_t t_count = 0;        // complex elements / component after the local transform [n0_loc][S1][S2e]
   int64_t fourier_count = 0;  // ... of the Fourier-side block [N0][n1_loc][S2e]
-  cufftHandle fwd_local = 0, inv_local = 0, axis0 = 0;
+  BatchFft fwd_local, inv_local;   // c2c: one plan serves both directions (inv_local unused)
+  cufftHandle axis0 = 0;
   bool have_local = false, have_axis0 = false;
   // single GPU, 3-D, fused axis-0 pass: the same local transforms writing / reading the k1-major
   // layout [k1][n0][S2e] through cuFFT's advanced data layout (created on first use)
-  cufftHandle fwd_local_t = 0, inv_local_t = 0;
+  BatchFft fwd_local_t, inv_local_t;
   bool have_local_t = false;
 };
 
@@ -419,6 +434,7 @@ struct bri17_rs_plan {
   cudaStream_t sx = nullptr;                      // exchange stream of the pipelined apply
   cudaEvent_t ev_a[3] = {}, ev_b[3] = {};         // per-component hand-offs st <-> sx
   int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
+  int fft_chunk_mib = 32;                         // local 2-D transforms run in L2-sized chunks of planes (BatchFft); 0 = whole slab
   int copy_ctas = 148 * 4;                        // grid cap of slab_copy_kernel
   double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components of the c2c layout each
   size_t buf_bytes = 0;
@@ -647,6 +663,59 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
   return launch_copy(cp, 0, st, p->copy_ctas);
 }
 
+// ---- chunked batched transforms (BatchFft) ---------------------------------------------------
+// Planes per chunk for a slab whose spectral planes hold `plane_elems` complex values.
+int chunk_planes(const bri17_rs_plan *p, long long plane_elems, long long real_plane, int planes) {
+  if (p->fft_chunk_mib <= 0 || planes <= 1) return std::max(planes, 1);
+  long long c = (static_cast<long long>(p->fft_chunk_mib) << 20) / std::max<long long>(plane_elems * 16, 1);
+  c = std::max<long long>(1, std::min<long long>(c, planes));
+  // real planes with an odd number of doubles: keep every chunk start 16-byte aligned
+  if ((real_plane & 1) && (c & 1) && c < planes) c = c > 1 ? c - 1 : 2;
+  return int(std::min<long long>(c, planes));
+}
+
+int batch_make(BatchFft &f, int rank, long long *n, long long *inembed, long long istride, long long idist,
+               long long *onembed, long long ostride, long long odist, cufftType type, int planes, int chunk) {
+  size_t ws = 0;
+  f.type = type;
+  f.idist = idist;
+  f.odist = odist;
+  f.chunk = std::max(1, std::min(chunk, planes));
+  f.nfull = planes / f.chunk;
+  f.rem = planes - f.nfull * f.chunk;
+  RS_CUFFT_TRY(cufftCreate(&f.h[0]));
+  RS_CUFFT_TRY(cufftMakePlanMany64(f.h[0], rank, n, inembed, istride, idist, onembed, ostride, odist, type, f.chunk, &ws));
+  if (f.rem) {
+    RS_CUFFT_TRY(cufftCreate(&f.h[1]));
+    RS_CUFFT_TRY(cufftMakePlanMany64(f.h[1], rank, n, inembed, istride, idist, onembed, ostride, odist, type, f.rem, &ws));
+  }
+  f.made = true;
+  return BRI17_OK;
+}
+
+void batch_destroy(BatchFft &f) {
+  if (f.h[0]) cufftDestroy(f.h[0]);
+  if (f.h[1]) cufftDestroy(f.h[1]);
+  f = BatchFft{};
+}
+
+// in / out: first plane of the component; dir is used by Z2Z only
+int batch_exec(const BatchFft &f, const void *in, void *out, int dir, cudaStream_t st) {
+  if (!f.made) return BRI17_OK;
+  const size_t isz = f.type == CUFFT_D2Z ? 8 : 16, osz = f.type == CUFFT_Z2D ? 8 : 16;
+  RS_CUFFT_TRY(cufftSetStream(f.h[0], st));
+  if (f.rem) RS_CUFFT_TRY(cufftSetStream(f.h[1], st));
+  for (int i = 0; i < f.nfull + (f.rem ? 1 : 0); i++) {
+    const cufftHandle h = i < f.nfull ? f.h[0] : f.h[1];
+    char *a = const_cast<char *>(static_cast<const char *>(in)) + size_t(i) * f.chunk * f.idist * isz;
+    char *b = static_cast<char *>(out) + size_t(i) * f.chunk * f.odist * osz;
+    if (f.type == CUFFT_Z2Z) RS_CUFFT_TRY(cufftExecZ2Z(h, (cufftDoubleComplex *)a, (cufftDoubleComplex *)b, dir));
+    else if (f.type == CUFFT_D2Z) RS_CUFFT_TRY(cufftExecD2Z(h, (cufftDoubleReal *)a, (cufftDoubleComplex *)b));
+    else RS_CUFFT_TRY(cufftExecZ2D(h, (cufftDoubleComplex *)a, (cufftDoubleReal *)b));
+  }
+  return BRI17_OK;
+}
+
 // c2c local transform over the trailing axes (complex layout only)
 int fft_local_c2c(bri17_rs_plan *p, const double2 *in, double2 *out, int ncomp, int dir, cudaStream_t st) {
   const Layout &l = p->lc;
@@ -655,10 +724,7 @@ int fft_local_c2c(bri17_rs_plan *p, const double2 *in, double2 *out, int ncomp, 
       BRI17_CUDA_TRY(cudaMemcpyAsync(out, in, sizeof(double2) * ncomp * l.t_count, cudaMemcpyDeviceToDevice, st));
     return BRI17_OK;
   }
-  RS_CUFFT_TRY(cufftSetStream(l.fwd_local, st));
-  for (int c = 0; c < ncomp; c++)
-    RS_CUFFT_TRY(cufftExecZ2Z(l.fwd_local, (cufftDoubleComplex *)(in + c * l.t_count),
-                              (cufftDoubleComplex *)(out + c * l.t_count), dir));
+  for (int c = 0; c < ncomp; c++) RS_TRY(batch_exec(l.fwd_local, in + c * l.t_count, out + c * l.t_count, dir, st));
   return BRI17_OK;
 }
 
@@ -707,18 +773,13 @@ int setup_layout(bri17_rs_plan *p, Layout &l) {
     long long n64[2] = {p->shape[1], p->N2e};
     const int frank = dim - 1;
     const long long rplane = (long long)p->shape[1] * p->N2e, splane = (long long)l.S1 * l.S2e;
+    // a 1-D transform (2-D grids) is a single kernel: nothing to gain from chunks
+    const int chunk = frank == 2 ? chunk_planes(p, splane, real ? rplane : 0, p->n0_loc) : p->n0_loc;
     if (!real) {
-      RS_CUFFT_TRY(cufftCreate(&l.fwd_local));
-      RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local, frank, n64, nullptr, 1, rplane, nullptr, 1, rplane,
-                                       CUFFT_Z2Z, p->n0_loc, &ws));
-      l.inv_local = l.fwd_local;
+      RS_TRY(batch_make(l.fwd_local, frank, n64, nullptr, 1, rplane, nullptr, 1, rplane, CUFFT_Z2Z, p->n0_loc, chunk));
     } else {
-      RS_CUFFT_TRY(cufftCreate(&l.fwd_local));
-      RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local, frank, n64, nullptr, 1, rplane, nullptr, 1, splane,
-                                       CUFFT_D2Z, p->n0_loc, &ws));
-      RS_CUFFT_TRY(cufftCreate(&l.inv_local));
-      RS_CUFFT_TRY(cufftMakePlanMany64(l.inv_local, frank, n64, nullptr, 1, splane, nullptr, 1, rplane,
-                                       CUFFT_Z2D, p->n0_loc, &ws));
+      RS_TRY(batch_make(l.fwd_local, frank, n64, nullptr, 1, rplane, nullptr, 1, splane, CUFFT_D2Z, p->n0_loc, chunk));
+      RS_TRY(batch_make(l.inv_local, frank, n64, nullptr, 1, splane, nullptr, 1, rplane, CUFFT_Z2D, p->n0_loc, chunk));
     }
     l.have_local = true;
   }
@@ -733,17 +794,15 @@ int setup_layout(bri17_rs_plan *p, Layout &l) {
   return BRI17_OK;
 }
 
+// Drops the cuFFT plans, keeps the geometry.
 void destroy_layout(Layout &l) {
-  if (l.have_local) {
-    cufftDestroy(l.fwd_local);
-    if (l.real) cufftDestroy(l.inv_local);
-  }
+  batch_destroy(l.fwd_local);
+  batch_destroy(l.inv_local);
   if (l.have_axis0) cufftDestroy(l.axis0);
-  if (l.have_local_t) {
-    cufftDestroy(l.fwd_local_t);
-    cufftDestroy(l.inv_local_t);
-  }
-  l = Layout{};
+  batch_destroy(l.fwd_local_t);
+  batch_destroy(l.inv_local_t);
+  l.axis0 = 0;
+  l.have_local = l.have_axis0 = l.have_local_t = l.ready = false;
 }
 
 // Exchange buffers: always present for P > 1 (allocated at creation so that their IPC
@@ -778,19 +837,17 @@ bool use_xt(const bri17_rs_plan *p, const Layout &l) {
 // element (k1, k2) of plane n0 at k1*(N0*S2e) + n0*S2e + k2.
 int setup_layout_t(bri17_rs_plan *p, Layout &l) {
   if (l.have_local_t || p->n0_loc == 0) return BRI17_OK;
-  size_t ws = 0;
   long long n64[2] = {p->shape[1], p->N2e};
   const long long rplane = (long long)p->shape[1] * p->N2e;
   long long nat[2] = {p->shape[1], p->N2e};                               // natural real-space planes
   long long spec[2] = {l.S1, (long long)p->shape[0] * l.S2e};            // k1 stride = N0*S2e
-  RS_CUFFT_TRY(cufftCreate(&l.fwd_local_t));
-  RS_CUFFT_TRY(cufftCreate(&l.inv_local_t));
+  const int chunk = chunk_planes(p, (long long)l.S1 * l.S2e, l.real ? rplane : 0, p->n0_loc);
   if (!l.real) {
-    RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local_t, 2, n64, nat, 1, rplane, spec, 1, l.S2e, CUFFT_Z2Z, p->n0_loc, &ws));
-    RS_CUFFT_TRY(cufftMakePlanMany64(l.inv_local_t, 2, n64, spec, 1, l.S2e, nat, 1, rplane, CUFFT_Z2Z, p->n0_loc, &ws));
+    RS_TRY(batch_make(l.fwd_local_t, 2, n64, nat, 1, rplane, spec, 1, l.S2e, CUFFT_Z2Z, p->n0_loc, chunk));
+    RS_TRY(batch_make(l.inv_local_t, 2, n64, spec, 1, l.S2e, nat, 1, rplane, CUFFT_Z2Z, p->n0_loc, chunk));
   } else {
-    RS_CUFFT_TRY(cufftMakePlanMany64(l.fwd_local_t, 2, n64, nat, 1, rplane, spec, 1, l.S2e, CUFFT_D2Z, p->n0_loc, &ws));
-    RS_CUFFT_TRY(cufftMakePlanMany64(l.inv_local_t, 2, n64, spec, 1, l.S2e, nat, 1, rplane, CUFFT_Z2D, p->n0_loc, &ws));
+    RS_TRY(batch_make(l.fwd_local_t, 2, n64, nat, 1, rplane, spec, 1, l.S2e, CUFFT_D2Z, p->n0_loc, chunk));
+    RS_TRY(batch_make(l.inv_local_t, 2, n64, spec, 1, l.S2e, nat, 1, rplane, CUFFT_Z2D, p->n0_loc, chunk));
   }
   l.have_local_t = true;
   return BRI17_OK;
@@ -1125,9 +1182,18 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
     std::memcpy(&id, nccl_unique_id, sizeof(id));
     ncclResult_t nr = ncclCommInitRank(&p->comm, nranks, id, rank);
     if (nr != ncclSuccess) return bail(fail(BRI17_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(nr)));
-    const size_t cap = std::max<size_t>(
-        sizeof(double2) * std::max<size_t>(size_t(dim) * size_t(std::max(p->lc.t_count, p->lc.fourier_count)),
-                                           2 * size_t(p->real_upper)), 16);
+    // Same size on EVERY rank (the largest any rank needs): the flag page sits right behind the
+    // data, and peers address it through their own copy of this number.
+    size_t cap_elems = 1;
+    for (int q = 0; q < nranks; q++) {
+      const size_t n0q = size_t(p->n0_beg[q + 1] - p->n0_beg[q]);
+      for (const Layout *l : {&p->lc, &p->lr}) {
+        const size_t n1q = size_t(l->k1_beg[q + 1] - l->k1_beg[q]);
+        const size_t t = n0q * l->S1 * l->S2e, f = size_t(shape[0]) * n1q * l->S2e;
+        cap_elems = std::max(cap_elems, size_t(dim) * std::max(t, f) * (l->real ? 2 : 1));
+      }
+    }
+    const size_t cap = sizeof(double2) * cap_elems;
     const size_t cap_pad = (cap + 255) & ~size_t(255);  // flag page behind the data, 256-byte aligned
     if (cudaMalloc(&p->W, cap_pad + FLAG_BYTES) != cudaSuccess || cudaMalloc(&p->W2, cap) != cudaSuccess ||
         cudaMalloc(&p->barrier_word, 256) != cudaSuccess)
@@ -1212,6 +1278,7 @@ int bri17_rs_forward_fft_f64(bri17_rs_plan *p, const void *x_dev, void *x_hat_de
   if (ncomp < 1) return fail(BRI17_ERR_INVALID_ARG, "ncomp < 1");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
+  if (!p->lc.ready) RS_TRY(setup_layout(p, p->lc));
   const Layout &l = p->lc;
   const double2 *x = static_cast<const double2 *>(x_dev);
   double2 *xh = static_cast<double2 *>(x_hat_dev);
@@ -1246,6 +1313,7 @@ int bri17_rs_inverse_fft_f64(bri17_rs_plan *p, void *x_hat_dev, void *x_dev, int
   if (ncomp < 1) return fail(BRI17_ERR_INVALID_ARG, "ncomp < 1");
   DeviceGuard guard(p->device);
   cudaStream_t st = cudaStream_t(stream);
+  if (!p->lc.ready) RS_TRY(setup_layout(p, p->lc));
   const Layout &l = p->lc;
   double2 *x = static_cast<double2 *>(x_dev);
   double2 *xh = static_cast<double2 *>(x_hat_dev);
@@ -1285,6 +1353,7 @@ int check_fields(const bri17_rs_plan *p, const void *a, const void *b) {
 
 int apply_complex(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st, double *dot_dev) {
   Layout &l = p->lc;
+  if (!l.ready) RS_TRY(setup_layout(p, l));
   const double2 *u = static_cast<const double2 *>(u_dev);
   double2 *F = static_cast<double2 *>(F_dev);
   const int dim = p->dim;
@@ -1302,22 +1371,14 @@ int apply_complex(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t
     RS_TRY(ensure_buffers(p, std::max<size_t>(sizeof(double2) * dim * l.t_count, 16)));
     double2 *X = p->W2;
     mark(p, 0, st);
-    if (l.have_local_t) {
-      RS_CUFFT_TRY(cufftSetStream(l.fwd_local_t, st));
-      for (int c = 0; c < dim; c++)
-        RS_CUFFT_TRY(cufftExecZ2Z(l.fwd_local_t, (cufftDoubleComplex *)(u + c * l.t_count),
-                                  (cufftDoubleComplex *)(X + c * l.t_count), CUFFT_FORWARD));
-    }
+    for (int c = 0; c < dim; c++)
+      RS_TRY(batch_exec(l.fwd_local_t, u + c * l.t_count, X + c * l.t_count, CUFFT_FORWARD, st));
     mark(p, 1, st);
     mark(p, 2, st);
     RS_TRY(modal_section(p, l, X, st, dot_dev, true));
     mark(p, 6, st);
-    if (l.have_local_t) {
-      RS_CUFFT_TRY(cufftSetStream(l.inv_local_t, st));
-      for (int c = 0; c < dim; c++)
-        RS_CUFFT_TRY(cufftExecZ2Z(l.inv_local_t, (cufftDoubleComplex *)(X + c * l.t_count),
-                                  (cufftDoubleComplex *)(F + c * l.t_count), CUFFT_INVERSE));
-    }
+    for (int c = 0; c < dim; c++)
+      RS_TRY(batch_exec(l.inv_local_t, X + c * l.t_count, F + c * l.t_count, CUFFT_INVERSE, st));
     mark(p, 7, st);
     p->timings_valid = true;
     return BRI17_OK;
@@ -1370,23 +1431,20 @@ int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st
   auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; };
   auto local_fwd = [&](int c) -> int {  // D2Z u_c -> T_c
     if (!l.have_local) return BRI17_OK;
-    const cufftHandle plan = local_t ? l.fwd_local_t : l.fwd_local;
-    RS_CUFFT_TRY(cufftSetStream(plan, st));
+    const BatchFft &plan = local_t ? l.fwd_local_t : l.fwd_local;
     double *src = const_cast<double *>(u) + c * p->real_count;
     if (misaligned(src)) {
       BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
       src = p->rbuf;
     }
-    RS_CUFFT_TRY(cufftExecD2Z(plan, src, (cufftDoubleComplex *)(T + c * l.t_count)));
-    return BRI17_OK;
+    return batch_exec(plan, src, T + c * l.t_count, 0, st);
   };
   auto local_inv = [&](int c) -> int {  // Z2D (W2)_c -> F_c
     if (!l.have_local) return BRI17_OK;
-    const cufftHandle plan = local_t ? l.inv_local_t : l.inv_local;
-    RS_CUFFT_TRY(cufftSetStream(plan, st));
+    const BatchFft &plan = local_t ? l.inv_local_t : l.inv_local;
     double *dst = F + c * p->real_count;
     double *out = misaligned(dst) ? p->rbuf : dst;
-    RS_CUFFT_TRY(cufftExecZ2D(plan, (cufftDoubleComplex *)(p->W2 + c * l.t_count), out));
+    RS_TRY(batch_exec(plan, p->W2 + c * l.t_count, out, 0, st));
     if (out != dst)
       BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
     return BRI17_OK;
@@ -1444,7 +1502,14 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
   if (!std::strcmp(key, "pipeline")) p->pipeline = value != 0;
   else if (!std::strcmp(key, "fused_axis0")) p->fused = value != 0;
   else if (!std::strcmp(key, "k1_major")) p->xt = value < 0 ? -1 : (value != 0);
-  else if (!std::strcmp(key, "copy_ctas")) {
+  else if (!std::strcmp(key, "fft_chunk_mib")) {
+    if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "fft_chunk_mib < 0");
+    DeviceGuard guard(p->device);
+    cudaDeviceSynchronize();
+    p->fft_chunk_mib = int(std::min<int64_t>(value, 1 << 20));
+    destroy_layout(p->lc);   // plans are rebuilt with the new chunk on next use
+    destroy_layout(p->lr);
+  } else if (!std::strcmp(key, "copy_ctas")) {
     if (value < 1) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 1");
     p->copy_ctas = int(value);
   } else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown option ") + key);
@@ -1459,6 +1524,8 @@ int bri17_rs_plan_get_info(const bri17_rs_plan *p, const char *key, int64_t *val
   else if (!std::strcmp(key, "fused_launches")) *value = p->fused_launches;
   else if (!std::strcmp(key, "pipeline")) *value = (p->nranks > 1 && p->mode == 1 && p->pipeline) ? 1 : 0;
   else if (!std::strcmp(key, "exchange_mode")) *value = p->mode;
+  else if (!std::strcmp(key, "fft_chunk_mib")) *value = p->fft_chunk_mib;
+  else if (!std::strcmp(key, "fft_chunk_planes")) *value = p->lc.fwd_local.made ? p->lc.fwd_local.chunk : 0;
   else if (!std::strcmp(key, "barriers")) *value = int64_t(p->epoch_bar[0] + p->epoch_bar[1]);
   else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown info key ") + key);
   return BRI17_OK;

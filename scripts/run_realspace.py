@@ -20,6 +20,7 @@ ap.add_argument("--real", action="store_true")
 ap.add_argument("--no-fused", action="store_true")
 ap.add_argument("--no-k1-major", action="store_true")
 ap.add_argument("--k1-major", action="store_true")
+ap.add_argument("--fft-chunk-mib", type=int, default=-1, help="chunk of the local 2-D transforms (0 = whole slab)")
 ap.add_argument("--cg", type=int, default=0, help="also time this many CG iterations")
 args = ap.parse_args()
 
@@ -32,6 +33,8 @@ if args.no_k1_major:
     op.set_option("k1_major", 0)
 if args.k1_major:
     op.set_option("k1_major", 1)
+if args.fft_chunk_mib >= 0:
+    op.set_option("fft_chunk_mib", args.fft_chunk_mib)
 if args.real:
     u = torch.randn(op.real_shape, dtype=torch.float64, device="cuda")
     fn = op.apply_real
@@ -50,6 +53,7 @@ e1.record()
 torch.cuda.synchronize()
 out = {"edge": args.edge, "real": args.real, "fused_axis0": bool(op.info("fused_axis0")),
        "k1_major": bool(op.info("k1_major_real" if args.real else "k1_major")),
+       "fft_chunk_mib": op.info("fft_chunk_mib"), "fft_chunk_planes": op.info("fft_chunk_planes"),
        "ms_per_apply": e0.elapsed_time(e1) / args.applies, "phases_ms": op.timings()}
 if args.cg:
     b = fn(u).clone()
