@@ -27,13 +27,17 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) axis0_fused_kernel(const 
     phase<C, DIM, 0>(tid, data, tw, p, col0, nx, dot);  // waits for this thread's async copies
     __syncthreads();
     phase<C, DIM, 1>(tid, data, tw, p, col0, nx, dot);
-    __syncthreads();
-    phase<C, DIM, 2>(tid, data, tw, p, col0, nx, dot);
     if constexpr (C::NPH > 3) {
-      __syncthreads();
+      // phases 1..3 of a warp touch only that warp's 64-row block (Cfg::WARP_LOCAL)
+      if constexpr (C::WARP_LOCAL) __syncwarp(); else __syncthreads();
+      phase<C, DIM, 2>(tid, data, tw, p, col0, nx, dot);
+      if constexpr (C::WARP_LOCAL) __syncwarp(); else __syncthreads();
       phase<C, DIM, 3>(tid, data, tw, p, col0, nx, dot);
       __syncthreads();
       phase<C, DIM, 4>(tid, data, tw, p, col0, nx, dot);
+    } else {
+      __syncthreads();
+      phase<C, DIM, 2>(tid, data, tw, p, col0, nx, dot);
     }
     // no barrier here: the next tile's first stage works on the slots this thread just used
   }
@@ -88,6 +92,8 @@ int launch(Params p, int dim, int sm_count, int max_grid, cudaStream_t st, int *
   if (!W) return fail(BRI17_ERR_UNSUPPORTED, "fused axis-0 pass: unsupported N0");
   p.n_tiles = (p.S + W - 1) / W;
   if (p.n_tiles == 0) { if (grid_out) *grid_out = 0; return BRI17_OK; }
+  if (p.S >= (1ll << 31) || p.blk_cols >= (1ll << 31))
+    return fail(BRI17_ERR_UNSUPPORTED, "fused axis-0 pass: more than 2^31 columns");
   switch (p.N0) {
     case 16: return launch_cfg<Cfg16>(p, dim, sm_count, max_grid, st, grid_out);
     case 32: return launch_cfg<Cfg32>(p, dim, sm_count, max_grid, st, grid_out);

@@ -218,16 +218,29 @@ A0_HD void cp_async16(double2 *smem_dst, const double2 *gsrc) {
   *smem_dst = *gsrc;
 #endif
 }
-A0_HD void cp_async_wait_all() {
+A0_HD void cp_async_commit() {
 #ifdef __CUDA_ARCH__
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+// waits until at most `pending` of this thread's most recent copy groups are still in flight
+A0_HD void cp_async_wait(int pending) {
+#ifdef __CUDA_ARCH__
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+  }
+#else
+  (void)pending;
 #endif
 }
 
-// Offset of column j (row n0 = 0) inside a component.
+// Offset of column j (row n0 = 0) inside a component.  Column counts fit 32 bits (checked by the
+// launcher): one 32-bit division instead of a 64-bit one per thread and tile.
 A0_HD long long col_base(const Params &p, long long j) {
-  const long long b = j / p.blk_cols;
-  return b * p.blk_stride + (j - b * p.blk_cols);
+  const unsigned ju = unsigned(j), bc = unsigned(p.blk_cols), b = ju / bc;
+  return (long long)b * p.blk_stride + (long long)(ju - b * bc);
 }
 
 // Configuration: N0 = R0*R1*R2 (R2 = 1: two stages), W columns per tile.
@@ -239,6 +252,12 @@ struct Cfg {
   static constexpr int NPH = 2 * NS - 1;                    // phases separated by CTA barriers
   static constexpr int THREADS = 256;
   static constexpr int MINB = (N0_ * W_ * 3 * 16 + N0_ * 16) <= 110 * 1024 ? 2 : 1;
+  // Three-stage plans with W <= 4: the 32 items of a warp are the 8 butterflies x W columns of ONE
+  // block of R1*R2 = 64 rows in the second stage, the middle phase and the second-to-last stage, so
+  // those phases only need a warp barrier between them: two CTA barriers per tile instead of four.
+  static constexpr bool WARP_LOCAL = R2_ == 8 && R1_ == 8 && W_ == 4;
+  // first-stage items per thread; 1: the loads of a tile are waited for component by component
+  static constexpr int ITEMS0 = (N0_ / R0_ * W_ + THREADS - 1) / THREADS;
   static constexpr size_t smem_bytes(int dim) { return size_t(N0_) * 16 + size_t(dim) * N0_ * W_ * 16; }
   // twiddle table (device array of N0 complex, staged in shared memory): stage 0 at [0], entry
   // (m-1)*stride0 + j = w_N0^(j m); stage 1 (three-stage plans) behind it, entry (m-1)*stride1 + j =
@@ -265,6 +284,7 @@ A0_HD void issue_tile_loads(int tid, double2 *data, const Params &p, long long c
     for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride) {
 #pragma unroll
       for (int r = 0; r < R; r++) cp_async16(d + row_of<W, stride>(nb, r) * W, g + (long long)r * stride * p.row_stride);
+      cp_async_commit();  // one group per component (see fwd_stage<FIRST>)
     }
   }
 }
@@ -276,7 +296,11 @@ A0_HD void issue_tile_loads(int tid, double2 *data, const Params &p, long long c
 template <class C, int DIM, int R, int BS, bool FIRST>
 A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p, long long col0) {
   constexpr int N0 = C::N0, W = C::W, stride = BS / R, nbf = N0 / R;
-  if constexpr (FIRST) cp_async_wait_all();
+  // FIRST: the copies were committed one group per component, in component order; with one item per
+  // thread component c is complete once at most DIM-1-c groups are pending, so the later components'
+  // copies stay in flight while the first ones are transformed
+  constexpr bool PER_COMP = FIRST && C::ITEMS0 == 1;
+  if constexpr (FIRST && !PER_COMP) cp_async_wait(0);
   for (int item = tid; item < nbf * W; item += C::THREADS) {
     const int w = item % W, q = item / W;
     if (col0 + w >= p.S) continue;
@@ -288,6 +312,7 @@ A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p
     double2 *d = data + w;
 #pragma unroll 1
     for (int c = 0; c < DIM; c++, d += N0 * W) {
+      if constexpr (PER_COMP) cp_async_wait(DIM - 1 - c);
       double2 a[R];
 #pragma unroll
       for (int r = 0; r < R; r++) a[r] = d[row_of<W, stride>(nb, r) * W];
@@ -331,6 +356,7 @@ A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p
           for (int r = 0; r < R; r++)
             cp_async16(d + row_of<W, stride>(nb, r) * W, gn + (long long)r * stride * p.row_stride);
         }
+        cp_async_commit();
       }
       if (!have) continue;
 #pragma unroll
@@ -345,31 +371,56 @@ A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p
   }
 }
 
-// K^ u of one mode from the per-axis factors, the reference's operation order
-// (bri17.hpp:268-274 / :276-288; product tests/test_bri17.cpp:68 / :84, left to right).
+// K^ u of one mode.  The factors that do not depend on k0 are combined once per column
+// (ColumnFactors, with |h|/|N| folded in); per mode that leaves 12 flops for the six distinct entries
+// of K^ (bri17.hpp:266-288) and 18 fused multiply-adds for the product (tests/test_bri17.cpp:68 / :84).
+// The products are re-associated with respect to the reference's written order: this path is
+// compared at 1e-13, not bitwise (an FFT is involved anyway); the bit-exact kernels are in
+// modal_kernels.cu.
 template <int DIM>
-A0_HD void stiffness_times(const double *phi, const double *chi, const double *psi, double mu, double scaling,
-                           const double2 *u, double2 *f) {
+struct ColumnFactors {
+  double a, b, c, d, e, g;  // 3-D: chi1 chi2, phi1 chi2, chi1 phi2, s psi1 chi2, s chi1 psi2, s psi1 psi2 (x out_scale)
+};
+
+template <int DIM>
+A0_HD ColumnFactors<DIM> column_factors(const double *phi, const double *chi, const double *psi, double scaling,
+                                        double out_scale) {
+  ColumnFactors<DIM> f;
   if constexpr (DIM == 3) {
-    const double H00 = (phi[0] * chi[1]) * chi[2];
-    const double H11 = (chi[0] * phi[1]) * chi[2];
-    const double H22 = (chi[0] * chi[1]) * phi[2];
-    const double Kd = mu * ((H00 + H11) + H22);
-    const double K00 = scaling * H00 + Kd, K11 = scaling * H11 + Kd, K22 = scaling * H22 + Kd;
-    const double K01 = ((scaling * psi[0]) * psi[1]) * chi[2];
-    const double K02 = ((scaling * psi[0]) * chi[1]) * psi[2];
-    const double K12 = ((scaling * chi[0]) * psi[1]) * psi[2];
-    f[0] = make_double2((K00 * u[0].x + K01 * u[1].x) + K02 * u[2].x, (K00 * u[0].y + K01 * u[1].y) + K02 * u[2].y);
-    f[1] = make_double2((K01 * u[0].x + K11 * u[1].x) + K12 * u[2].x, (K01 * u[0].y + K11 * u[1].y) + K12 * u[2].y);
-    f[2] = make_double2((K02 * u[0].x + K12 * u[1].x) + K22 * u[2].x, (K02 * u[0].y + K12 * u[1].y) + K22 * u[2].y);
+    const double c2 = chi[2] * out_scale, sp1 = scaling * psi[1];
+    f.a = chi[1] * c2;
+    f.b = phi[1] * c2;
+    f.c = chi[1] * (phi[2] * out_scale);
+    f.d = sp1 * c2;
+    f.e = (scaling * chi[1]) * (psi[2] * out_scale);
+    f.g = sp1 * (psi[2] * out_scale);
   } else {
-    const double H00 = phi[0] * chi[1];
-    const double H11 = chi[0] * phi[1];
+    f.a = chi[1] * out_scale;
+    f.b = phi[1] * out_scale;
+    f.d = (scaling * psi[1]) * out_scale;
+    f.c = f.e = f.g = 0.;
+  }
+  return f;
+}
+
+template <int DIM>
+A0_HD void stiffness_times(double phi0, double chi0, double psi0, const ColumnFactors<DIM> &cf, double mu,
+                           double scaling, const double2 *u, double2 *f) {
+  if constexpr (DIM == 3) {
+    const double H00 = phi0 * cf.a, H11 = chi0 * cf.b, H22 = chi0 * cf.c;
+    const double Kd = mu * ((H00 + H11) + H22);
+    const double K00 = fma_(scaling, H00, Kd), K11 = fma_(scaling, H11, Kd), K22 = fma_(scaling, H22, Kd);
+    const double K01 = psi0 * cf.d, K02 = psi0 * cf.e, K12 = chi0 * cf.g;
+    f[0] = make_double2(fma_(K02, u[2].x, fma_(K01, u[1].x, K00 * u[0].x)), fma_(K02, u[2].y, fma_(K01, u[1].y, K00 * u[0].y)));
+    f[1] = make_double2(fma_(K12, u[2].x, fma_(K11, u[1].x, K01 * u[0].x)), fma_(K12, u[2].y, fma_(K11, u[1].y, K01 * u[0].y)));
+    f[2] = make_double2(fma_(K22, u[2].x, fma_(K12, u[1].x, K02 * u[0].x)), fma_(K22, u[2].y, fma_(K12, u[1].y, K02 * u[0].y)));
+  } else {
+    const double H00 = phi0 * cf.a, H11 = chi0 * cf.b;
     const double Kd = mu * (H00 + H11);
-    const double K00 = scaling * H00 + Kd, K11 = scaling * H11 + Kd;
-    const double K01 = (scaling * psi[0]) * psi[1];
-    f[0] = make_double2(K00 * u[0].x + K01 * u[1].x, K00 * u[0].y + K01 * u[1].y);
-    f[1] = make_double2(K01 * u[0].x + K11 * u[1].x, K01 * u[0].y + K11 * u[1].y);
+    const double K00 = fma_(scaling, H00, Kd), K11 = fma_(scaling, H11, Kd);
+    const double K01 = psi0 * cf.d;
+    f[0] = make_double2(fma_(K01, u[1].x, K00 * u[0].x), fma_(K01, u[1].y, K00 * u[0].y));
+    f[1] = make_double2(fma_(K11, u[1].x, K01 * u[0].x), fma_(K11, u[1].y, K01 * u[0].y));
   }
 }
 
@@ -406,36 +457,39 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
     else kbase = q;
     double phi[3], chi[3], psi[3];
     int k_last;
+    const unsigned colu = unsigned(col);  // column counts fit 32 bits (launcher)
     if constexpr (DIM == 3) {
-      const int b = int(col / p.S2e), k2 = int(col - (long long)b * p.S2e), k1 = p.k1_begin + b;
+      const unsigned b = colu / unsigned(p.S2e);
+      const int k2 = int(colu - b * unsigned(p.S2e)), k1 = p.k1_begin + int(b);
       phi[1] = ld_tab(p.tab1 + k1); chi[1] = ld_tab(p.tab1 + p.N1 + k1); psi[1] = ld_tab(p.tab1 + 2 * p.N1 + k1);
       phi[2] = ld_tab(p.tab2 + k2); chi[2] = ld_tab(p.tab2 + p.N2 + k2); psi[2] = ld_tab(p.tab2 + 2 * p.N2 + k2);
       k_last = k2;
     } else {
-      const int k1 = p.k1_begin + int(col);
+      const int k1 = p.k1_begin + int(colu);
       phi[1] = ld_tab(p.tab1 + k1); chi[1] = ld_tab(p.tab1 + p.N1 + k1); psi[1] = ld_tab(p.tab1 + 2 * p.N1 + k1);
+      phi[2] = chi[2] = psi[2] = 0.;
       k_last = k1;
     }
+    const ColumnFactors<DIM> cf = column_factors<DIM>(phi, chi, psi, p.scaling, p.out_scale);
     const double wgt = (p.herm_n > 0 && k_last != 0 && 2 * k_last != p.herm_n) ? 2. : 1.;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const int k0 = kbase + r * nbf;
-      phi[0] = ld_tab(p.tab0 + k0); chi[0] = ld_tab(p.tab0 + N0 + k0); psi[0] = ld_tab(p.tab0 + 2 * N0 + k0);
+      const double phi0 = ld_tab(p.tab0 + k0), chi0 = ld_tab(p.tab0 + N0 + k0), psi0 = ld_tab(p.tab0 + 2 * N0 + k0);
       double2 u[DIM], f[DIM];
 #pragma unroll
       for (int c = 0; c < DIM - 1; c++) u[c] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
       u[DIM - 1] = last[r];
-      stiffness_times<DIM>(phi, chi, psi, p.mu, p.scaling, u, f);
-#pragma unroll
-      for (int c = 0; c < DIM; c++) { f[c].x *= p.out_scale; f[c].y *= p.out_scale; }
+      stiffness_times<DIM>(phi0, chi0, psi0, cf, p.mu, p.scaling, u, f);
 #pragma unroll
       for (int c = 0; c < DIM - 1; c++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = f[c];
       last[r] = f[DIM - 1];
       if (p.dot_partial) {
-        double dd = u[0].x * f[0].x + u[0].y * f[0].y;
+        double dd = u[0].x * f[0].x;
+        dd = fma_(u[0].y, f[0].y, dd);
 #pragma unroll
-        for (int c = 1; c < DIM; c++) dd += u[c].x * f[c].x + u[c].y * f[c].y;
-        dot_acc += wgt * dd;
+        for (int c = 1; c < DIM; c++) { dd = fma_(u[c].x, f[c].x, dd); dd = fma_(u[c].y, f[c].y, dd); }
+        dot_acc = fma_(wgt, dd, dot_acc);
       }
     }
     // first inverse stage (stride 1, no twiddle before it): the register-resident component first

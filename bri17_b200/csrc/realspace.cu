@@ -384,12 +384,14 @@ __global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double *x, do
 
 }  // namespace
 
-// Batched transform over the trailing axes of a slab, one plane per batch entry, executed in CHUNKS
-// of consecutive planes.  cuFFT runs a 2-D transform as two kernels (one per axis) with the whole
-// batch between them: over a 512^3 component that is two full passes over HBM.  With a chunk that
-// fits the 126 MB L2 the second kernel finds the first one's output there and overwrites it in
-// place before it is evicted, so the pair costs about ONE read and ONE write of the data
-// (option "fft_chunk_mib"; measured in profiles/r02_measurements.md).
+// Batched transform over the trailing axes of a slab, one plane per batch entry, optionally executed
+// in CHUNKS of consecutive planes (option "fft_chunk_mib").  cuFFT runs a 2-D transform as two kernels
+// (one per axis) with the whole batch between them: over a 512^3 component that is two full passes over
+// HBM, each at the copy roofline (0.62-0.78 ms for 4.3 GB).  The idea of the chunks: with a chunk that
+// fits the 126 MB L2 the second kernel could find the first one's output there.  MEASURED (512^3, one
+// B200, profiles/r02_measurements.md): it does not pay -- 4.8 ms per direction for the whole slab, 7.0 ms
+// with 32 MiB chunks, 5.8 ms with 96 MiB chunks (hundreds of 20 us kernels with dependent launches lose
+// more than the L2 hits win).  Default: one chunk = the whole slab.
 struct BatchFft {
   cufftHandle h[2] = {0, 0};        // [0] chunks of `chunk` planes, [1] the remaining `rem` planes
   int chunk = 0, nfull = 0, rem = 0;
@@ -434,7 +436,7 @@ struct bri17_rs_plan {
   cudaStream_t sx = nullptr;                      // exchange stream of the pipelined apply
   cudaEvent_t ev_a[3] = {}, ev_b[3] = {};         // per-component hand-offs st <-> sx
   int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
-  int fft_chunk_mib = 32;                         // local 2-D transforms run in L2-sized chunks of planes (BatchFft); 0 = whole slab
+  int fft_chunk_mib = 0;                          // > 0: local 2-D transforms run in chunks of planes of this size (BatchFft); measured slower, off
   int copy_ctas = 148 * 4;                        // grid cap of slab_copy_kernel
   double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components of the c2c layout each
   size_t buf_bytes = 0;

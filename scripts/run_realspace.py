@@ -15,6 +15,7 @@ from bri17_b200.realspace import RealSpaceOperator  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--edge", type=int, default=512)
+ap.add_argument("--shape", type=str, default="", help="N0,N1,N2 (overrides --edge)")
 ap.add_argument("--applies", type=int, default=3)
 ap.add_argument("--real", action="store_true")
 ap.add_argument("--no-fused", action="store_true")
@@ -24,7 +25,7 @@ ap.add_argument("--fft-chunk-mib", type=int, default=-1, help="chunk of the loca
 ap.add_argument("--cg", type=int, default=0, help="also time this many CG iterations")
 args = ap.parse_args()
 
-shape = (args.edge,) * 3
+shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else (args.edge,) * 3
 L = tuple(n * h for n, h in zip(shape, (1.1, 1.2, 1.3)))
 op = RealSpaceOperator(shape, L, 5.6, 0.3)
 if args.no_fused:
@@ -51,7 +52,7 @@ for _ in range(args.applies):
     fn(u, out=F)
 e1.record()
 torch.cuda.synchronize()
-out = {"edge": args.edge, "real": args.real, "fused_axis0": bool(op.info("fused_axis0")),
+out = {"shape": list(shape), "real": args.real, "fused_axis0": bool(op.info("fused_axis0")),
        "k1_major": bool(op.info("k1_major_real" if args.real else "k1_major")),
        "fft_chunk_mib": op.info("fft_chunk_mib"), "fft_chunk_planes": op.info("fft_chunk_planes"),
        "ms_per_apply": e0.elapsed_time(e1) / args.applies, "phases_ms": op.timings()}
