@@ -75,6 +75,7 @@ using bri17b200::fail;
 namespace {
 
 constexpr int MAX_RANKS = 16;
+constexpr int MAX_XCHUNKS = 4;  // sub-slabs per component in the pipelined apply
 
 // One family of equal-length row pieces to move: for c < ncomp, a < rows, e < len:
 //   dst[c*dst_cs + a*dst_rs + off(e, dst_bs)] = scale * src[c*src_cs + a*src_rs + off(e, src_bs)]
@@ -393,10 +394,15 @@ __global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(double *x, do
 // with 32 MiB chunks, 5.8 ms with 96 MiB chunks (hundreds of 20 us kernels with dependent launches lose
 // more than the L2 hits win).  Default: one chunk = the whole slab.
 struct BatchFft {
-  cufftHandle h[2] = {0, 0};        // [0] chunks of `chunk` planes, [1] the remaining `rem` planes
-  int chunk = 0, nfull = 0, rem = 0;
+  int rank = 0;
+  long long n[2] = {1, 1}, inembed[2] = {1, 1}, onembed[2] = {1, 1};
+  bool embed = false;               // advanced layout (inembed/onembed) or the packed default
+  long long istride = 1, ostride = 1;
   long long idist = 0, odist = 0;   // elements of the input / output type between consecutive planes
   cufftType type = CUFFT_Z2Z;
+  int planes = 0, chunk = 0;        // planes of the slab; planes per cuFFT call in batch_exec
+  struct { int batch; cufftHandle h; } cache[8] = {};  // one cuFFT plan per batch size in use
+  int ncache = 0;
   bool made = false;
 };
 
@@ -434,7 +440,8 @@ struct bri17_rs_plan {
   bri17_plan *modal = nullptr;
   ncclComm_t comm = nullptr;
   cudaStream_t sx = nullptr;                      // exchange stream of the pipelined apply
-  cudaEvent_t ev_a[3] = {}, ev_b[3] = {};         // per-component hand-offs st <-> sx
+  cudaEvent_t ev_a[3 * MAX_XCHUNKS] = {}, ev_b[3 * MAX_XCHUNKS] = {};  // per-sub-slab hand-offs st <-> sx
+  int xchunks = 0;                                // option "exchange_chunks": sub-slabs per component (0 = by size)
   int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
   int fft_chunk_mib = 0;                          // > 0: local 2-D transforms run in chunks of planes of this size (BatchFft); measured slower, off
   int copy_ctas = 148 * 4;                        // grid cap of slab_copy_kernel
@@ -519,8 +526,9 @@ int scalar_allreduce(bri17_rs_plan *p, double *v, int n, cudaStream_t st) {
 // -> Fourier-side layout X[c][n0][b_loc][k2].  `S` is the packed send buffer (mode 0).
 // c0/ncomp select components of the multi-component arrays T and X; `barriers` = false leaves
 // the cross-GPU synchronisation to the caller (pipelined apply).
+// a0/na (mode 1 only): restrict the exchange to planes [a0, a0 + na) of this rank's n0 slab (na < 0: all).
 int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double2 *X, double2 *S, int ncomp,
-                     cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false) {
+                     cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false, int a0 = 0, int na = -1) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   CopyPlan cp{};
   cp.ncomp = ncomp;
@@ -559,8 +567,14 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
       g.dst_cs = (long long)p->n0_loc * n1q * S2e;
       g.dst_rs = (long long)n1q * S2e;
     }
+    if (na >= 0) {  // sub-slab of planes
+      if (na == 0) { cp.nseg--; continue; }
+      g.rows = na;
+      g.src += (long long)a0 * g.src_rs;
+      g.dst += (long long)a0 * g.dst_rs;
+    }
   }
-  cp.parts = choose_parts(maxlen, (long long)ncomp * p->n0_loc * P);
+  cp.parts = choose_parts(maxlen, (long long)ncomp * (na >= 0 ? na : p->n0_loc) * P);
   if (p->mode == 1 && barriers) RS_TRY(stream_barrier(p, st));  // peers' buffers are free to overwrite
   RS_TRY(launch_copy(cp, p->mode == 1, st, p->copy_ctas));
   if (P == 1) return BRI17_OK;
@@ -583,8 +597,11 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
 
 // Backward exchange: Fourier-side X[c][n0][b_loc][k2] -> local-transform layout D[c][a][b][k2] (times scale).
 // mode 0: R = packed receive buffer, D written by the unpack; mode 1: peers store into our W2 (= D).
+// chunk/nchunks (mode 1 only): restrict the exchange to the chunk-th of nchunks parts of EVERY
+// destination's n0 slab (planes [n0q*chunk/nchunks, n0q*(chunk+1)/nchunks) of rank q).
 int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, double2 *D, double2 *R, int ncomp,
-                      double scale, cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false) {
+                      double scale, cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false,
+                      int chunk = 0, int nchunks = 1) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   if (p->mode == 1 || P == 1) {
     // every row (c, n0) goes, whole, to the owner of n0, at its final position
@@ -613,8 +630,15 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
       g.dst_cs = (long long)n0q * S1 * S2e;
       g.dst_rs = (long long)S1 * S2e;
       g.dst = base + (long long)l.k1_beg[r] * S2e + c0 * g.dst_cs;
+      if (nchunks > 1) {
+        const int a0 = int((long long)n0q * chunk / nchunks), a1 = int((long long)n0q * (chunk + 1) / nchunks);
+        if (a1 == a0) { cp.nseg--; continue; }
+        g.rows = a1 - a0;
+        g.src += (long long)a0 * g.src_rs;
+        g.dst += (long long)a0 * g.dst_rs;
+      }
     }
-    cp.parts = choose_parts(l.n1_loc * S2e, (long long)ncomp * N0);
+    cp.parts = choose_parts(l.n1_loc * S2e, (long long)ncomp * N0 / nchunks);
     if (barriers) RS_TRY(stream_barrier(p, st));
     RS_TRY(launch_copy(cp, P > 1, st, p->copy_ctas));
     return barriers ? stream_barrier(p, st) : BRI17_OK;
@@ -676,51 +700,83 @@ int chunk_planes(const bri17_rs_plan *p, long long plane_elems, long long real_p
   return int(std::min<long long>(c, planes));
 }
 
-int batch_make(BatchFft &f, int rank, long long *n, long long *inembed, long long istride, long long idist,
-               long long *onembed, long long ostride, long long odist, cufftType type, int planes, int chunk) {
+int batch_handle(BatchFft &f, int batch, cufftHandle *out) {
+  for (int i = 0; i < f.ncache; i++)
+    if (f.cache[i].batch == batch) { *out = f.cache[i].h; return BRI17_OK; }
+  if (f.ncache == 8) return fail(BRI17_ERR_UNSUPPORTED, "too many distinct batch sizes for one transform");
   size_t ws = 0;
-  f.type = type;
-  f.idist = idist;
-  f.odist = odist;
-  f.chunk = std::max(1, std::min(chunk, planes));
-  f.nfull = planes / f.chunk;
-  f.rem = planes - f.nfull * f.chunk;
-  RS_CUFFT_TRY(cufftCreate(&f.h[0]));
-  RS_CUFFT_TRY(cufftMakePlanMany64(f.h[0], rank, n, inembed, istride, idist, onembed, ostride, odist, type, f.chunk, &ws));
-  if (f.rem) {
-    RS_CUFFT_TRY(cufftCreate(&f.h[1]));
-    RS_CUFFT_TRY(cufftMakePlanMany64(f.h[1], rank, n, inembed, istride, idist, onembed, ostride, odist, type, f.rem, &ws));
+  cufftHandle h = 0;
+  RS_CUFFT_TRY(cufftCreate(&h));
+  cufftResult r = cufftMakePlanMany64(h, f.rank, f.n, f.embed ? f.inembed : nullptr, f.istride, f.idist,
+                                      f.embed ? f.onembed : nullptr, f.ostride, f.odist, f.type, batch, &ws);
+  if (r != CUFFT_SUCCESS) {
+    cufftDestroy(h);
+    return fail(BRI17_ERR_CUDA, "cufftMakePlanMany64: cuFFT error " + std::to_string(int(r)));
   }
-  f.made = true;
+  f.cache[f.ncache].batch = batch;
+  f.cache[f.ncache].h = h;
+  f.ncache++;
+  *out = h;
   return BRI17_OK;
 }
 
+int batch_make(BatchFft &f, int rank, const long long *n, const long long *inembed, long long istride, long long idist,
+               const long long *onembed, long long ostride, long long odist, cufftType type, int planes, int chunk) {
+  f = BatchFft{};
+  f.rank = rank;
+  for (int i = 0; i < rank; i++) {
+    f.n[i] = n[i];
+    if (inembed) f.inembed[i] = inembed[i];
+    if (onembed) f.onembed[i] = onembed[i];
+  }
+  f.embed = inembed != nullptr;
+  f.istride = istride; f.ostride = ostride;
+  f.idist = idist; f.odist = odist;
+  f.type = type;
+  f.planes = planes;
+  f.chunk = std::max(1, std::min(chunk, planes));
+  f.made = true;
+  cufftHandle h;
+  return batch_handle(f, f.chunk, &h);  // the plan every full chunk uses, created up front
+}
+
 void batch_destroy(BatchFft &f) {
-  if (f.h[0]) cufftDestroy(f.h[0]);
-  if (f.h[1]) cufftDestroy(f.h[1]);
+  for (int i = 0; i < f.ncache; i++) cufftDestroy(f.cache[i].h);
   f = BatchFft{};
 }
 
-// in / out: first plane of the component; dir is used by Z2Z only
-int batch_exec(const BatchFft &f, const void *in, void *out, int dir, cudaStream_t st) {
-  if (!f.made) return BRI17_OK;
+// `na` planes, in / out pointing AT the first of them; dir is used by Z2Z only.
+int batch_exec_at(BatchFft &f, const void *in, void *out, int na, int dir, cudaStream_t st) {
+  if (!f.made || na <= 0) return BRI17_OK;
+  cufftHandle h;
+  RS_TRY(batch_handle(f, na, &h));
+  RS_CUFFT_TRY(cufftSetStream(h, st));
+  void *a = const_cast<void *>(in), *b = out;
+  if (f.type == CUFFT_Z2Z) RS_CUFFT_TRY(cufftExecZ2Z(h, (cufftDoubleComplex *)a, (cufftDoubleComplex *)b, dir));
+  else if (f.type == CUFFT_D2Z) RS_CUFFT_TRY(cufftExecD2Z(h, (cufftDoubleReal *)a, (cufftDoubleComplex *)b));
+  else RS_CUFFT_TRY(cufftExecZ2D(h, (cufftDoubleComplex *)a, (cufftDoubleReal *)b));
+  return BRI17_OK;
+}
+
+// Planes [a0, a0 + na) of the component whose first plane is at in / out.
+int batch_exec_range(BatchFft &f, const void *in, void *out, int a0, int na, int dir, cudaStream_t st) {
+  if (!f.made || na <= 0) return BRI17_OK;
   const size_t isz = f.type == CUFFT_D2Z ? 8 : 16, osz = f.type == CUFFT_Z2D ? 8 : 16;
-  RS_CUFFT_TRY(cufftSetStream(f.h[0], st));
-  if (f.rem) RS_CUFFT_TRY(cufftSetStream(f.h[1], st));
-  for (int i = 0; i < f.nfull + (f.rem ? 1 : 0); i++) {
-    const cufftHandle h = i < f.nfull ? f.h[0] : f.h[1];
-    char *a = const_cast<char *>(static_cast<const char *>(in)) + size_t(i) * f.chunk * f.idist * isz;
-    char *b = static_cast<char *>(out) + size_t(i) * f.chunk * f.odist * osz;
-    if (f.type == CUFFT_Z2Z) RS_CUFFT_TRY(cufftExecZ2Z(h, (cufftDoubleComplex *)a, (cufftDoubleComplex *)b, dir));
-    else if (f.type == CUFFT_D2Z) RS_CUFFT_TRY(cufftExecD2Z(h, (cufftDoubleReal *)a, (cufftDoubleComplex *)b));
-    else RS_CUFFT_TRY(cufftExecZ2D(h, (cufftDoubleComplex *)a, (cufftDoubleReal *)b));
-  }
+  return batch_exec_at(f, static_cast<const char *>(in) + size_t(a0) * f.idist * isz,
+                       static_cast<char *>(out) + size_t(a0) * f.odist * osz, na, dir, st);
+}
+
+// The whole slab of one component, `chunk` planes per call.
+int batch_exec(BatchFft &f, const void *in, void *out, int dir, cudaStream_t st) {
+  if (!f.made) return BRI17_OK;
+  for (int a0 = 0; a0 < f.planes; a0 += f.chunk)
+    RS_TRY(batch_exec_range(f, in, out, a0, std::min(f.chunk, f.planes - a0), dir, st));
   return BRI17_OK;
 }
 
 // c2c local transform over the trailing axes (complex layout only)
 int fft_local_c2c(bri17_rs_plan *p, const double2 *in, double2 *out, int ncomp, int dir, cudaStream_t st) {
-  const Layout &l = p->lc;
+  Layout &l = p->lc;
   if (!l.have_local) {
     if (in != out && l.t_count)
       BRI17_CUDA_TRY(cudaMemcpyAsync(out, in, sizeof(double2) * ncomp * l.t_count, cudaMemcpyDeviceToDevice, st));
@@ -1001,24 +1057,74 @@ int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long
   return BRI17_OK;
 }
 
-// Pipelined apply for nranks > 1 with the fused peer-store exchange: the exchange of
-// component c runs on its own high-priority stream while the transforms of the other
-// components run on the caller's stream, so NVLink-bound and HBM-bound work overlap.
-//   st: L0 L1 L2 |wait| A0 A1 A2  modal  A'0 A'1 A'2 |wait| L'0 L'1 L'2
-//   sx:    P0 P1 P2 (push + barrier each)        Q0 Q1 Q2 (push back + barrier each)
-// L = local transform over the trailing axes, A = axis-0 transform, P/Q = slab_copy_kernel
-// storing into the peers' W / W2.  No "buffer free" barrier is needed: every exchange ends
-// with a barrier after its last read, and the next writer is ordered behind it.
+// Pipelined apply for nranks > 1 with the fused peer-store exchange: the exchange runs on its own
+// high-priority stream while the transforms run on the caller's stream, so NVLink-bound and
+// HBM-bound work overlap.  The unit of the pipeline is a SUB-SLAB: J chunks of n0 planes per
+// component (J = exchange_chunks(): 1..4, larger for larger slabs).
+//   st: L00 L01 .. L2J |wait| fused axis-0 pass |      wait Q00: L'00, wait Q01: L'01 ...
+//   sx:     P00 P01 ..  P2J, barrier            | Q00 b Q01 b ... Q2J b
+// L = local transform over the trailing axes of a sub-slab, P/Q = slab_copy_kernel storing into the
+// peers' W / W2 (b = flag barrier).  Only the last P and the first Q are exposed: 1/(3J) of each
+// exchange (round 1 pipelined whole components: 1/3).  The forward direction needs ONE barrier (its
+// consumer, the axis-0 pass, needs every piece anyway); backward, the consumer of sub-slab (c, j) is
+// the local inverse transform of exactly those planes, so every Q is followed by a barrier.
+// No "buffer free" barrier is needed: every exchange ends with a barrier after its last read, and
+// the next writer is ordered behind it.
+// Without the fused axis-0 pass (cuFFT per component) the schedule is per component, as in round 1:
+//   st: L0 L1 L2 |wait 0| A0 |wait 1| A1 A2  modal  A'0 A'1 A'2      |wait| L'0 L'1 L'2
+//   sx:    P0b P1b P2b                               Q0b Q1b Q2b
+int exchange_chunks(const bri17_rs_plan *p, const Layout &l) {
+  if (p->xchunks > 0) return std::min(p->xchunks, MAX_XCHUNKS);
+  const long long bytes = 16ll * l.t_count;  // one component of the slab
+  return int(std::max<long long>(1, std::min<long long>(MAX_XCHUNKS, bytes >> 27)));  // >= 128 MiB per sub-slab
+}
+
 template <typename LocalFwd, typename LocalInv>
 int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFwd local_fwd, LocalInv local_inv,
                     cudaStream_t st, double *dot_dev) {
   const int dim = p->dim;
   double2 *X = p->W;
   const bool xt = use_xt(p, l);
+  const bool fused = use_fused(p);
   p->timings_valid = false;
   mark(p, 0, st);
+  if (fused || dot_dev) {
+    const int J = exchange_chunks(p, l);
+    auto lo = [&](int j) { return int((long long)p->n0_loc * j / J); };
+    for (int c = 0; c < dim; c++)
+      for (int j = 0; j < J; j++) {
+        const int e = c * J + j, a0 = lo(j), na = lo(j + 1) - a0;
+        RS_TRY(local_fwd(c, a0, na));
+        BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[e], st));
+        BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[e], 0));
+        RS_TRY(exchange_forward(p, l, T, X, nullptr, 1, p->sx, c, false, xt, a0, na));
+      }
+    RS_TRY(exchange_barrier(p));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[0], p->sx));
+    mark(p, 1, st);
+    mark(p, 2, st);
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[0], 0));
+    RS_TRY(modal_section(p, l, X, st, dot_dev, xt));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[0], st));
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[0], 0));
+    for (int c = 0; c < dim; c++)
+      for (int j = 0; j < J; j++) {
+        RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false, xt, j, J));
+        RS_TRY(exchange_barrier(p));
+        BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c * J + j], p->sx));
+      }
+    mark(p, 6, st);
+    for (int c = 0; c < dim; c++)
+      for (int j = 0; j < J; j++) {
+        BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c * J + j], 0));
+        RS_TRY(local_inv(c, lo(j), lo(j + 1) - lo(j)));
+      }
+    mark(p, 7, st);
+    p->timings_valid = true;
+    return BRI17_OK;
+  }
   for (int c = 0; c < dim; c++) {
-    RS_TRY(local_fwd(c));
+    RS_TRY(local_fwd(c, 0, p->n0_loc));
     BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
     BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
     RS_TRY(exchange_forward(p, l, T, X, nullptr, 1, p->sx, c, false, xt));
@@ -1027,43 +1133,29 @@ int apply_pipelined(bri17_rs_plan *p, const Layout &l, const double2 *T, LocalFw
   }
   mark(p, 1, st);
   mark(p, 2, st);
-  const bool fused = use_fused(p);
-  if (fused || dot_dev) {
-    // the axis-0 section needs every component: wait for the three forward exchanges
-    for (int c = 0; c < dim; c++) BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
-    RS_TRY(modal_section(p, l, X, st, dot_dev, xt));
-    for (int c = 0; c < dim; c++) {
-      if (c == 0) BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[0], st));
-      BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[0], 0));
-      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false, xt));
-      RS_TRY(exchange_barrier(p));
-      BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
-    }
-  } else {
-    for (int c = 0; c < dim; c++) {
-      BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
-      RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_FORWARD, st));
-    }
-    mark(p, 3, st);
-    int kb[3] = {0, l.k1_beg[p->rank], 0};
-    int ls[3] = {p->shape[0], l.n1_loc, l.S2e};
-    if (l.fourier_count)
-      RS_TRY(bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st));
-    mark(p, 4, st);
-    for (int c = 0; c < dim; c++) {
-      RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_INVERSE, st));
-      BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
-      BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
-      RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
-      RS_TRY(exchange_barrier(p));
-      BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
-    }
-    mark(p, 5, st);
+  for (int c = 0; c < dim; c++) {
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
+    RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_FORWARD, st));
   }
+  mark(p, 3, st);
+  int kb[3] = {0, l.k1_beg[p->rank], 0};
+  int ls[3] = {p->shape[0], l.n1_loc, l.S2e};
+  if (l.fourier_count)
+    RS_TRY(bri17_modal_stiffness_apply_f64(p->modal, X, X, kb, ls, 0, p->correction, st));
+  mark(p, 4, st);
+  for (int c = 0; c < dim; c++) {
+    RS_TRY(fft_axis0(p, l, X + c * l.fourier_count, 1, CUFFT_INVERSE, st));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_a[c], st));
+    BRI17_CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_a[c], 0));
+    RS_TRY(exchange_backward(p, l, X, p->W2, nullptr, 1, 1.0, p->sx, c, false));
+    RS_TRY(exchange_barrier(p));
+    BRI17_CUDA_TRY(cudaEventRecord(p->ev_b[c], p->sx));
+  }
+  mark(p, 5, st);
   mark(p, 6, st);
   for (int c = 0; c < dim; c++) {
     BRI17_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_b[c], 0));
-    RS_TRY(local_inv(c));
+    RS_TRY(local_inv(c, 0, p->n0_loc));
   }
   mark(p, 7, st);
   p->timings_valid = true;
@@ -1208,7 +1300,7 @@ int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shape, const d
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
       if (cudaStreamCreateWithPriority(&p->sx, cudaStreamNonBlocking, hi) != cudaSuccess)
         return bail(fail(BRI17_ERR_CUDA, "exchange stream creation failed"));
-      for (int c = 0; c < 3; c++)
+      for (int c = 0; c < 3 * MAX_XCHUNKS; c++)
         if (cudaEventCreateWithFlags(&p->ev_a[c], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&p->ev_b[c], cudaEventDisableTiming) != cudaSuccess)
           return bail(fail(BRI17_ERR_CUDA, "cudaEventCreate failed"));
@@ -1361,8 +1453,12 @@ int apply_complex(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t
   const int dim = p->dim;
   const bool xt = use_xt(p, l);
   if (p->nranks > 1 && p->mode == 1 && p->pipeline) {
-    auto fwd = [&](int c) { return fft_local_c2c(p, u + c * l.t_count, F + c * l.t_count, 1, CUFFT_FORWARD, st); };
-    auto inv = [&](int c) { return fft_local_c2c(p, p->W2 + c * l.t_count, F + c * l.t_count, 1, CUFFT_INVERSE, st); };
+    auto fwd = [&](int c, int a0, int na) {
+      return batch_exec_range(l.fwd_local, u + c * l.t_count, F + c * l.t_count, a0, na, CUFFT_FORWARD, st);
+    };
+    auto inv = [&](int c, int a0, int na) {
+      return batch_exec_range(l.fwd_local, p->W2 + c * l.t_count, F + c * l.t_count, a0, na, CUFFT_INVERSE, st);
+    };
     return apply_pipelined(p, l, F, fwd, inv, st, dot_dev);
   }
   p->timings_valid = false;
@@ -1431,31 +1527,38 @@ int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st
   // is misaligned when the slab holds an odd number of values: stage those through rbuf.
   if ((p->real_count & 1) && !p->rbuf) BRI17_CUDA_TRY(cudaMalloc(&p->rbuf, sizeof(double) * (p->real_count + 2)));
   auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) != 0; };
-  auto local_fwd = [&](int c) -> int {  // D2Z u_c -> T_c
-    if (!l.have_local) return BRI17_OK;
-    const BatchFft &plan = local_t ? l.fwd_local_t : l.fwd_local;
-    double *src = const_cast<double *>(u) + c * p->real_count;
+  const long long rplane = (long long)p->shape[1] * p->N2e;  // doubles per real-space plane
+  auto local_fwd = [&](int c, int a0, int na) -> int {  // D2Z planes [a0, a0 + na) of u_c -> T_c
+    if (!l.have_local || na <= 0) return BRI17_OK;
+    BatchFft &plan = local_t ? l.fwd_local_t : l.fwd_local;
+    const double *src = u + c * p->real_count + a0 * rplane;
     if (misaligned(src)) {
-      BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
+      BRI17_CUDA_TRY(cudaMemcpyAsync(p->rbuf, src, sizeof(double) * na * rplane, cudaMemcpyDeviceToDevice, st));
       src = p->rbuf;
     }
-    return batch_exec(plan, src, T + c * l.t_count, 0, st);
+    return batch_exec_at(plan, src, T + c * l.t_count + a0 * plan.odist, na, 0, st);
   };
-  auto local_inv = [&](int c) -> int {  // Z2D (W2)_c -> F_c
-    if (!l.have_local) return BRI17_OK;
-    const BatchFft &plan = local_t ? l.inv_local_t : l.inv_local;
-    double *dst = F + c * p->real_count;
+  auto local_inv = [&](int c, int a0, int na) -> int {  // Z2D planes [a0, a0 + na) of (W2)_c -> F_c
+    if (!l.have_local || na <= 0) return BRI17_OK;
+    BatchFft &plan = local_t ? l.inv_local_t : l.inv_local;
+    double *dst = F + c * p->real_count + a0 * rplane;
     double *out = misaligned(dst) ? p->rbuf : dst;
-    RS_TRY(batch_exec(plan, p->W2 + c * l.t_count, out, 0, st));
+    RS_TRY(batch_exec_at(plan, p->W2 + c * l.t_count + a0 * plan.idist, out, na, 0, st));
     if (out != dst)
-      BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * p->real_count, cudaMemcpyDeviceToDevice, st));
+      BRI17_CUDA_TRY(cudaMemcpyAsync(dst, out, sizeof(double) * na * rplane, cudaMemcpyDeviceToDevice, st));
+    return BRI17_OK;
+  };
+  // the whole slab of component c, in the plan's chunks (one chunk unless "fft_chunk_mib" is set)
+  auto whole = [&](auto &fn, BatchFft &plan, int c) -> int {
+    const int step = plan.made ? plan.chunk : std::max(p->n0_loc, 1);
+    for (int a0 = 0; a0 < p->n0_loc; a0 += step) RS_TRY(fn(c, a0, std::min(step, p->n0_loc - a0)));
     return BRI17_OK;
   };
   if (p->nranks > 1 && p->mode == 1 && p->pipeline) return apply_pipelined(p, l, T, local_fwd, local_inv, st, dot_dev);
 
   p->timings_valid = false;
   mark(p, 0, st);
-  for (int c = 0; c < dim; c++) RS_TRY(local_fwd(c));
+  for (int c = 0; c < dim; c++) RS_TRY(whole(local_fwd, local_t ? l.fwd_local_t : l.fwd_local, c));
   mark(p, 1, st);
   double2 *X = T;
   if (p->nranks > 1) {
@@ -1474,7 +1577,7 @@ int apply_real(bri17_rs_plan *p, const void *u_dev, void *F_dev, cudaStream_t st
     }
   }
   mark(p, 6, st);
-  for (int c = 0; c < dim; c++) RS_TRY(local_inv(c));
+  for (int c = 0; c < dim; c++) RS_TRY(whole(local_inv, local_t ? l.inv_local_t : l.inv_local, c));
   mark(p, 7, st);
   p->timings_valid = true;
   return BRI17_OK;
@@ -1504,7 +1607,10 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
   if (!std::strcmp(key, "pipeline")) p->pipeline = value != 0;
   else if (!std::strcmp(key, "fused_axis0")) p->fused = value != 0;
   else if (!std::strcmp(key, "k1_major")) p->xt = value < 0 ? -1 : (value != 0);
-  else if (!std::strcmp(key, "fft_chunk_mib")) {
+  else if (!std::strcmp(key, "exchange_chunks")) {
+    if (value < 0 || value > MAX_XCHUNKS) return fail(BRI17_ERR_INVALID_ARG, "exchange_chunks must be 0 (auto) .. 4");
+    p->xchunks = int(value);
+  } else if (!std::strcmp(key, "fft_chunk_mib")) {
     if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "fft_chunk_mib < 0");
     DeviceGuard guard(p->device);
     cudaDeviceSynchronize();
@@ -1527,6 +1633,8 @@ int bri17_rs_plan_get_info(const bri17_rs_plan *p, const char *key, int64_t *val
   else if (!std::strcmp(key, "pipeline")) *value = (p->nranks > 1 && p->mode == 1 && p->pipeline) ? 1 : 0;
   else if (!std::strcmp(key, "exchange_mode")) *value = p->mode;
   else if (!std::strcmp(key, "fft_chunk_mib")) *value = p->fft_chunk_mib;
+  else if (!std::strcmp(key, "exchange_chunks")) *value = exchange_chunks(p, p->lc);
+  else if (!std::strcmp(key, "exchange_chunks_real")) *value = exchange_chunks(p, p->lr);
   else if (!std::strcmp(key, "fft_chunk_planes")) *value = p->lc.fwd_local.made ? p->lc.fwd_local.chunk : 0;
   else if (!std::strcmp(key, "barriers")) *value = int64_t(p->epoch_bar[0] + p->epoch_bar[1]);
   else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown info key ") + key);

@@ -96,6 +96,15 @@ def main():
             report(f"{tag} {shape}: fft layout/apply", err, 1e-13)
             report(f"{tag} {shape}: CG ({iters} it) solution error", cg_err, 1e-7)
             report(f"{tag} {shape}: CG residual", res, 1e-11)
+    # sub-slab pipelining forced to 3 and 4 pieces per component on slabs of a few planes (empty and
+    # uneven sub-slabs included), fused pass (power-of-two N0) and cuFFT axis-0 path
+    for chunks in (3, 4):
+        report(f"pipelined apply in {chunks} sub-slabs per component: small grids",
+               rc.small_grids(local, 1, 1, 1, chunks=chunks), 1e-13)
+    report("pipelined apply in 4 sub-slabs: dense KAT, real fields",
+           rc.dense_kat(local, world, mode=1, pipeline=1, real=True, chunks=4), 0.0)
+    report("pipelined apply in 3 sub-slabs: 128^3 distributed vs single-GPU slabs",
+           rc.vs_single_gpu(local, edge=128, chunks=3), 1e-13)
     # the reference's dense-matrix known-answer test with compute_Ku on all ranks
     # (tests/test_bri17.cpp:130-150); value = worst violation of 1e-15*|e| + 1e-14, 0 = none
     report("dense KAT (3,4,5) + rank-divisible grid, complex fields, fused exchange",

@@ -45,9 +45,10 @@ def _max_over_ranks(value, device):
     return float(t.item())
 
 
-def _make(shape, L, mu, nu, local_rank, mode, pipeline=None, fused=None):
+def _make(shape, L, mu, nu, local_rank, mode, pipeline=None, fused=None, chunks=None):
     """fused: 1 = fused axis-0 pass on the k1-major layout (default), 2 = fused pass on the natural
-    layout, 0 = cuFFT + modal kernel + cuFFT."""
+    layout, 0 = cuFFT + modal kernel + cuFFT.  chunks: sub-slabs per component of the pipelined
+    apply (None = the plan's own choice by size)."""
     from bri17_b200.realspace import RealSpaceOperator
     op = RealSpaceOperator.from_process_group(shape, L, mu, nu, device=local_rank, exchange_mode=mode)
     if pipeline is not None:
@@ -55,11 +56,13 @@ def _make(shape, L, mu, nu, local_rank, mode, pipeline=None, fused=None):
     if fused is not None:
         op.set_option("fused_axis0", 1 if fused else 0)
         op.set_option("k1_major", 1 if fused == 1 else 0)
+    if chunks is not None:
+        op.set_option("exchange_chunks", chunks)
     return op
 
 
 def small_grids(local_rank, mode=1, pipeline=1, fused=1, mu=5.6, nu=0.3,
-                shapes=((66, 60, 50), (3, 4, 5), (32, 32, 32), (64, 20, 18), (12, 10), (64, 48))):
+                shapes=((66, 60, 50), (3, 4, 5), (32, 32, 32), (64, 20, 18), (12, 10), (64, 48)), chunks=None):
     """Distributed apply (complex + real fields, applied twice: buffer reuse) against the numpy
     restatement.  (66, 60, 50) divides by no rank count; (3, 4, 5) leaves ranks without rows when
     world > 3 (and without k1 columns when world > 4)."""
@@ -76,7 +79,7 @@ def small_grids(local_rank, mode=1, pipeline=1, fused=1, mu=5.6, nu=0.3,
         u = rng.standard_normal((dim,) + shape)
         ref = real_space_apply_ref(o, shape, L, mu, nu, u + 0j)
         scale = np.abs(ref).max()
-        op = _make(shape, L, mu, nu, local_rank, mode, pipeline, fused)
+        op = _make(shape, L, mu, nu, local_rank, mode, pipeline, fused, chunks)
         a0, a1 = op.n0_begin, op.n0_begin + op.n0_count
         uc = torch.from_numpy(np.ascontiguousarray(u[:, a0:a1]) + 0j).to(dev)
         ur = torch.from_numpy(np.ascontiguousarray(u[:, a0:a1])).to(dev)
@@ -95,7 +98,7 @@ def small_grids(local_rank, mode=1, pipeline=1, fused=1, mu=5.6, nu=0.3,
     return _max_over_ranks(worst, dev)
 
 
-def dense_kat(local_rank, world, mode=1, pipeline=1, real=False):
+def dense_kat(local_rank, world, mode=1, pipeline=1, real=False, chunks=None):
     """Column j of the dense stiffness matrix = distributed real_space_apply(e_j), compared entry
     by entry with the classical FE assembly of the Maxima element matrix at the reference's
     tolerance 1e-15*|e| + 1e-14; the reference's own grid (3, 4, 5) -- zero-row slabs for
@@ -109,7 +112,7 @@ def dense_kat(local_rank, world, mode=1, pipeline=1, real=False):
     for shape in ((3, 4, 5), (n, n, 5)):
         dim = 3
         L = tuple(float(m) * h for m, h in zip(shape, kat.SPACING[3]))
-        op = _make(shape, L, kat.MU, kat.NU, local_rank, mode, pipeline)
+        op = _make(shape, L, kat.MU, kat.NU, local_rank, mode, pipeline, chunks=chunks)
         a0, cnt = op.n0_begin, op.n0_count
         size = int(np.prod(shape))
         plane = shape[1] * shape[2]
@@ -142,7 +145,7 @@ def dense_kat(local_rank, world, mode=1, pipeline=1, real=False):
     return _max_over_ranks(worst, dev)      # <= 0 means every entry is within the reference tolerance
 
 
-def vs_single_gpu(local_rank, edge=256, mode=1, mu=5.6, nu=0.3):
+def vs_single_gpu(local_rank, edge=256, mode=1, mu=5.6, nu=0.3, chunks=None):
     """Distributed apply on an edge^3 grid against this rank's slab of a SINGLE-GPU apply of the
     same field (generated from one seed on every rank)."""
     import torch
@@ -155,7 +158,7 @@ def vs_single_gpu(local_rank, edge=256, mode=1, mu=5.6, nu=0.3):
     single = RealSpaceOperator(shape, L, mu, nu, device=local_rank)
     F1 = single.apply_real(u)
     single.close()
-    op = _make(shape, L, mu, nu, local_rank, mode)
+    op = _make(shape, L, mu, nu, local_rank, mode, chunks=chunks)
     a0, a1 = op.n0_begin, op.n0_begin + op.n0_count
     us = u[:, a0:a1].contiguous()
     Fr = op.apply_real(us)
