@@ -244,9 +244,12 @@ A0_HD long long col_base(const Params &p, long long j) {
 }
 
 // Configuration: N0 = R0*R1*R2 (R2 = 1: two stages), W columns per tile.
-template <int N0_, int W_, int R0_, int R1_, int R2_>
+template <int N0_, int W_, int R0_, int R1_, int R2_, int KEEP_ = 1>
 struct Cfg {
   static constexpr int N0 = N0_, W = W_, R0 = R0_, R1 = R1_, R2 = R2_;
+  // components whose RL values stay in REGISTERS from the last forward stage through K^ to the first
+  // inverse stage (the others make three round trips through shared memory in the middle phase)
+  static constexpr int KEEP = KEEP_;
   static constexpr int NS = R2_ == 1 ? 2 : 3;
   static constexpr int RL = NS == 3 ? R2_ : R1_;            // radix of the last (stride-1) stage
   static constexpr int NPH = 2 * NS - 1;                    // phases separated by CTA barriers
@@ -310,17 +313,43 @@ A0_HD void fwd_stage(int tid, double2 *data, const double2 *tws, const Params &p
 #pragma unroll
     for (int m = 1; m < R; m++) t[m - 1] = tws[(m - 1) * stride + j];
     double2 *d = data + w;
-#pragma unroll 1
-    for (int c = 0; c < DIM; c++, d += N0 * W) {
-      if constexpr (PER_COMP) cp_async_wait(DIM - 1 - c);
-      double2 a[R];
+    if constexpr (R <= 8) {
+      // software pipeline over the components: the shared-memory loads of component c+1 are issued
+      // before the butterflies of component c (short-scoreboard stalls were the top stall reason)
+      double2 a[R], nx[R] = {};
+      if constexpr (PER_COMP) cp_async_wait(DIM - 1);
 #pragma unroll
       for (int r = 0; r < R; r++) a[r] = d[row_of<W, stride>(nb, r) * W];
-      Dft<R, false>::run(a);
 #pragma unroll
-      for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, t[m - 1].y);
+      for (int c = 0; c < DIM; c++) {
+        if (c + 1 < DIM) {
+          if constexpr (PER_COMP) cp_async_wait(DIM - 2 - c);
 #pragma unroll
-      for (int m = 0; m < R; m++) d[row_of<W, stride>(nb, m) * W] = a[m];
+          for (int r = 0; r < R; r++) nx[r] = d[((c + 1) * N0 + row_of<W, stride>(nb, r)) * W];
+        }
+        Dft<R, false>::run(a);
+#pragma unroll
+        for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, t[m - 1].y);
+#pragma unroll
+        for (int m = 0; m < R; m++) d[(c * N0 + row_of<W, stride>(nb, m)) * W] = a[m];
+        if (c + 1 < DIM) {
+#pragma unroll
+          for (int r = 0; r < R; r++) a[r] = nx[r];
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < DIM; c++, d += N0 * W) {
+        if constexpr (PER_COMP) cp_async_wait(DIM - 1 - c);
+        double2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) a[r] = d[row_of<W, stride>(nb, r) * W];
+        Dft<R, false>::run(a);
+#pragma unroll
+        for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, t[m - 1].y);
+#pragma unroll
+        for (int m = 0; m < R; m++) d[row_of<W, stride>(nb, m) * W] = a[m];
+      }
     }
   }
 }
@@ -345,27 +374,66 @@ A0_HD void inv_stage(int tid, double2 *data, const double2 *tws, const Params &p
     double2 *g = p.X + (have ? col_base(p, col0 + w) : 0) + (long long)nb * p.row_stride;
     const double2 *gn = p.X + (more ? col_base(p, next_col0 + w) : 0) + (long long)nb * p.row_stride;
     double2 *d = data + w;
-#pragma unroll 1
-    for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride, gn += p.comp_stride) {
-      double2 a[R];
+    if constexpr (R <= 8) {
+      // software pipeline over the components (see fwd_stage); LAST: the slots of a component are
+      // refilled with the next tile's inputs right after they have been read
+      double2 a[R], nx[R] = {};
+      auto fetch = [&](double2 (&v)[R], int c) {
 #pragma unroll
-      for (int m = 0; m < R; m++) a[m] = have ? d[row_of<W, stride>(nb, m) * W] : make_double2(0., 0.);
-      if constexpr (LAST) {
-        if (more) {
+        for (int m = 0; m < R; m++)
+          v[m] = have ? d[(c * N0 + row_of<W, stride>(nb, m)) * W] : make_double2(0., 0.);
+        if constexpr (LAST) {
+          if (more) {
 #pragma unroll
-          for (int r = 0; r < R; r++)
-            cp_async16(d + row_of<W, stride>(nb, r) * W, gn + (long long)r * stride * p.row_stride);
+            for (int r = 0; r < R; r++)
+              cp_async16(d + (c * N0 + row_of<W, stride>(nb, r)) * W,
+                         gn + c * p.comp_stride + (long long)r * stride * p.row_stride);
+          }
+          cp_async_commit();
         }
-        cp_async_commit();
+      };
+      fetch(a, 0);
+#pragma unroll
+      for (int c = 0; c < DIM; c++) {
+        if (c + 1 < DIM) fetch(nx, c + 1);
+        if (have) {
+#pragma unroll
+          for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, -t[m - 1].y);
+          Dft<R, true>::run(a);
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (LAST) st_stream(g + c * p.comp_stride + (long long)r * stride * p.row_stride, a[r]);
+            else d[(c * N0 + row_of<W, stride>(nb, r)) * W] = a[r];
+          }
+        }
+        if (c + 1 < DIM) {
+#pragma unroll
+          for (int r = 0; r < R; r++) a[r] = nx[r];
+        }
       }
-      if (!have) continue;
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < DIM; c++, d += N0 * W, g += p.comp_stride, gn += p.comp_stride) {
+        double2 a[R];
 #pragma unroll
-      for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, -t[m - 1].y);
-      Dft<R, true>::run(a);
+        for (int m = 0; m < R; m++) a[m] = have ? d[row_of<W, stride>(nb, m) * W] : make_double2(0., 0.);
+        if constexpr (LAST) {
+          if (more) {
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (LAST) st_stream(g + (long long)r * stride * p.row_stride, a[r]);
-        else d[row_of<W, stride>(nb, r) * W] = a[r];
+            for (int r = 0; r < R; r++)
+              cp_async16(d + row_of<W, stride>(nb, r) * W, gn + (long long)r * stride * p.row_stride);
+          }
+          cp_async_commit();
+        }
+        if (!have) continue;
+#pragma unroll
+        for (int m = 1; m < R; m++) a[m] = cmul(a[m], t[m - 1].x, -t[m - 1].y);
+        Dft<R, true>::run(a);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (LAST) st_stream(g + (long long)r * stride * p.row_stride, a[r]);
+          else d[row_of<W, stride>(nb, r) * W] = a[r];
+        }
       }
     }
   }
@@ -436,10 +504,11 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
     if (col >= p.S) continue;
     const int nb = q * R;
     double2 *d = data + w;
-    // last forward stage (no twiddle after it); the LAST component stays in registers
-    double2 last[R];
+    // last forward stage (no twiddle after it); the last KEEP components stay in registers
+    constexpr int KEEP = C::KEEP < DIM ? C::KEEP : DIM, VIA = DIM - KEEP;
+    double2 keep[KEEP][R];
 #pragma unroll 1
-    for (int c = 0; c < DIM - 1; c++) {
+    for (int c = 0; c < VIA; c++) {
       double2 a[R];
 #pragma unroll
       for (int r = 0; r < R; r++) a[r] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
@@ -448,8 +517,11 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
       for (int r = 0; r < R; r++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = a[r];
     }
 #pragma unroll
-    for (int r = 0; r < R; r++) last[r] = d[((DIM - 1) * N0 + row_of<W, 1>(nb, r)) * W];
-    Dft<R, false>::run(last);
+    for (int kc = 0; kc < KEEP; kc++) {
+#pragma unroll
+      for (int r = 0; r < R; r++) keep[kc][r] = d[((VIA + kc) * N0 + row_of<W, 1>(nb, r)) * W];
+      Dft<R, false>::run(keep[kc]);
+    }
     // position nb + r holds frequency k0 = kbase + r * (N0 / R): digits of q, least significant
     // stage first (decimation in frequency leaves the spectrum in digit-reversed order)
     int kbase;
@@ -478,12 +550,14 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
       const double phi0 = ld_tab(p.tab0 + k0), chi0 = ld_tab(p.tab0 + N0 + k0), psi0 = ld_tab(p.tab0 + 2 * N0 + k0);
       double2 u[DIM], f[DIM];
 #pragma unroll
-      for (int c = 0; c < DIM - 1; c++) u[c] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
-      u[DIM - 1] = last[r];
+      for (int c = 0; c < VIA; c++) u[c] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
+#pragma unroll
+      for (int kc = 0; kc < KEEP; kc++) u[VIA + kc] = keep[kc][r];
       stiffness_times<DIM>(phi0, chi0, psi0, cf, p.mu, p.scaling, u, f);
 #pragma unroll
-      for (int c = 0; c < DIM - 1; c++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = f[c];
-      last[r] = f[DIM - 1];
+      for (int c = 0; c < VIA; c++) d[(c * N0 + row_of<W, 1>(nb, r)) * W] = f[c];
+#pragma unroll
+      for (int kc = 0; kc < KEEP; kc++) keep[kc][r] = f[VIA + kc];
       if (p.dot_partial) {
         double dd = u[0].x * f[0].x;
         dd = fma_(u[0].y, f[0].y, dd);
@@ -492,12 +566,15 @@ A0_HD void mid_phase(int tid, double2 *data, const Params &p, long long col0, do
         dot_acc = fma_(wgt, dd, dot_acc);
       }
     }
-    // first inverse stage (stride 1, no twiddle before it): the register-resident component first
-    Dft<R, true>::run(last);
+    // first inverse stage (stride 1, no twiddle before it): the register-resident components first
 #pragma unroll
-    for (int r = 0; r < R; r++) d[((DIM - 1) * N0 + row_of<W, 1>(nb, r)) * W] = last[r];
+    for (int kc = 0; kc < KEEP; kc++) {
+      Dft<R, true>::run(keep[kc]);
+#pragma unroll
+      for (int r = 0; r < R; r++) d[((VIA + kc) * N0 + row_of<W, 1>(nb, r)) * W] = keep[kc][r];
+    }
 #pragma unroll 1
-    for (int c = 0; c < DIM - 1; c++) {
+    for (int c = 0; c < VIA; c++) {
       double2 a[R];
 #pragma unroll
       for (int r = 0; r < R; r++) a[r] = d[(c * N0 + row_of<W, 1>(nb, r)) * W];
@@ -569,8 +646,8 @@ using Cfg32 = Cfg<32, 64, 4, 8, 1>;
 using Cfg64 = Cfg<64, 32, 8, 8, 1>;
 using Cfg128 = Cfg<128, 16, 2, 8, 8>;
 using Cfg256 = Cfg<256, 8, 4, 8, 8>;
-using Cfg512 = Cfg<512, 4, 8, 8, 8>;
-using Cfg1024 = Cfg<1024, 4, 16, 8, 8>;
+using Cfg512 = Cfg<512, 4, 8, 8, 8, 2>;
+using Cfg1024 = Cfg<1024, 4, 16, 8, 8, 3>;
 
 inline bool supported(int N0) {
   return N0 == 16 || N0 == 32 || N0 == 64 || N0 == 128 || N0 == 256 || N0 == 512 || N0 == 1024;
