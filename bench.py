@@ -288,6 +288,7 @@ def realspace_records(args, torch, dist, local_rank, rank, world, dev):
         op = RealSpaceOperator.from_process_group(shape, L, MU, NU, device=local_rank, exchange_mode=1)
         rec["fused_axis0_kernel"] = bool(op.info("fused_axis0"))
         rec["pipelined"] = bool(op.info("pipeline"))
+        rec["sub_slabs_per_component"] = {"complex": op.info("exchange_chunks"), "real": op.info("exchange_chunks_real")}
         for real in (False, True):
             key = "real_fields_r2c" if real else "complex_fields_c2c"
             ms, phases = timed_apply(op, real, args.rs_steps, 2)

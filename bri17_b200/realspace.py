@@ -71,7 +71,8 @@ class RealSpaceOperator:
         check(self._lib.bri17_rs_plan_set_option(self._plan, key.encode(), int(value)))
 
     def info(self, key):
-        """"fused_axis0", "fused_launches", "pipeline", "exchange_mode", "barriers"."""
+        """"fused_axis0", "k1_major", "k1_major_real", "fused_launches", "pipeline", "exchange_mode",
+        "exchange_chunks", "exchange_chunks_real", "fft_chunk_mib", "fft_chunk_planes", "barriers"."""
         v = C.c_int64()
         check(self._lib.bri17_rs_plan_get_info(self._plan, key.encode(), C.byref(v)))
         return v.value

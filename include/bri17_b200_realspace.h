@@ -58,8 +58,11 @@ BRI17_API int bri17_rs_plan_create(bri17_rs_plan **out, int dim, const int *shap
                                    const void *nccl_unique_id, int exchange_mode);
 BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
 
-/* Tuning knobs: "pipeline" (1 = overlap the exchange of one component with the
- * transforms of the others on a second stream; default 1, fused exchange only),
+/* Tuning knobs: "pipeline" (1 = overlap the exchange with the local transforms on a second
+ * stream, sub-slab by sub-slab; default 1, fused exchange only), "exchange_chunks" (sub-slabs of
+ * n0 planes per component in that pipeline: 1..4, 0 = by size, at least 128 MiB each; default 0),
+ * "fft_chunk_mib" (> 0: run the local 2-D transforms in chunks of planes of this size so that
+ * cuFFT's second kernel could hit L2; measured slower at every size, default 0 = whole slab),
  * "copy_ctas" (grid cap of the exchange kernel), "fused_axis0" (1 = run FFT(axis 0) ->
  * K^ -> inverse FFT(axis 0) as one kernel when shape[0] is 16..1024 and a power of two;
  * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths),
