@@ -443,6 +443,7 @@ struct bri17_rs_plan {
   cudaEvent_t ev_a[3 * MAX_XCHUNKS] = {}, ev_b[3 * MAX_XCHUNKS] = {};  // per-sub-slab hand-offs st <-> sx
   int xchunks = 0;                                // option "exchange_chunks": sub-slabs per component (0 = by size)
   int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
+  int fft_chunk_planes = 0;                       // same in planes (takes precedence; tests)
   int fft_chunk_mib = 0;                          // > 0: local 2-D transforms run in chunks of planes of this size (BatchFft); measured slower, off
   int copy_ctas = 148 * 4;                        // grid cap of slab_copy_kernel
   double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components of the c2c layout each
@@ -692,8 +693,10 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
 // ---- chunked batched transforms (BatchFft) ---------------------------------------------------
 // Planes per chunk for a slab whose spectral planes hold `plane_elems` complex values.
 int chunk_planes(const bri17_rs_plan *p, long long plane_elems, long long real_plane, int planes) {
-  if (p->fft_chunk_mib <= 0 || planes <= 1) return std::max(planes, 1);
-  long long c = (static_cast<long long>(p->fft_chunk_mib) << 20) / std::max<long long>(plane_elems * 16, 1);
+  if ((p->fft_chunk_mib <= 0 && p->fft_chunk_planes <= 0) || planes <= 1) return std::max(planes, 1);
+  long long c = p->fft_chunk_planes > 0
+                    ? p->fft_chunk_planes
+                    : (static_cast<long long>(p->fft_chunk_mib) << 20) / std::max<long long>(plane_elems * 16, 1);
   c = std::max<long long>(1, std::min<long long>(c, planes));
   // real planes with an odd number of doubles: keep every chunk start 16-byte aligned
   if ((real_plane & 1) && (c & 1) && c < planes) c = c > 1 ? c - 1 : 2;

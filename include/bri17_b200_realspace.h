@@ -62,7 +62,8 @@ BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
  * stream, sub-slab by sub-slab; default 1, fused exchange only), "exchange_chunks" (sub-slabs of
  * n0 planes per component in that pipeline: 1..4, 0 = by size, at least 128 MiB each; default 0),
  * "fft_chunk_mib" (> 0: run the local 2-D transforms in chunks of planes of this size so that
- * cuFFT's second kernel could hit L2; measured slower at every size, default 0 = whole slab),
+ * cuFFT's second kernel could hit L2; measured slower at every size, default 0 = whole slab;
+ * "fft_chunk_planes": the same in planes),
  * "copy_ctas" (grid cap of the exchange kernel), "fused_axis0" (1 = run FFT(axis 0) ->
  * K^ -> inverse FFT(axis 0) as one kernel when shape[0] is 16..1024 and a power of two;
  * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths),

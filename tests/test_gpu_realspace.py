@@ -205,6 +205,34 @@ def test_apply_with_dot(oracle_mod, shape, fused):
     assert abs(dotc - expect) <= 1e-12 * expect
 
 
+@pytest.mark.parametrize("shape", [(16, 12, 10), (7, 5, 3), (9, 6, 7), (12, 10), (32, 8, 6)])
+@pytest.mark.parametrize("k1_major", [0, 1])
+def test_local_transforms_in_chunks_of_planes(oracle_mod, shape, k1_major):
+    """Option "fft_chunk_mib": the local transforms run plane range by plane range through the
+    per-batch-size plan cache (the machinery the multi-GPU sub-slab pipeline uses).  With chunks of a
+    single plane (two when the real planes hold an odd number of doubles: 16-byte alignment) the
+    result must equal the whole-slab transform bit for bit, complex and real fields, natural and
+    k1-major spectral layouts."""
+    dim = len(shape)
+    L = spacing_L(shape)
+    rng = np.random.default_rng(7)
+    u = torch.from_numpy(rng.standard_normal((dim,) + shape)).cuda()
+    whole = RealSpaceOperator(shape, L, MU, NU)
+    whole.set_option("k1_major", k1_major)
+    chunked = RealSpaceOperator(shape, L, MU, NU)
+    chunked.set_option("k1_major", k1_major)
+    chunked.set_option("fft_chunk_planes", 1)          # "fft_chunk_mib" gives the same in MiB
+    Fw, Fc = whole.apply(u + 0j), chunked.apply(u + 0j)
+    # (a 1-D local transform -- 2-D grids -- is a single cuFFT kernel and is never split)
+    assert chunked.info("fft_chunk_planes") == (1 if dim == 3 else shape[0])
+    assert whole.info("fft_chunk_planes") == shape[0]
+    assert torch.equal(Fw, Fc)
+    Rw, Rc = whole.apply_real(u), chunked.apply_real(u)
+    assert torch.equal(Rw, Rc)
+    ref = real_space_apply_ref(oracle_mod.best(), shape, L, MU, NU, u.cpu().numpy() + 0j)
+    assert np.abs(Rc.cpu().numpy() - ref.real).max() <= 1e-13 * np.abs(ref).max()
+
+
 def test_cg_projects_out_the_null_space(oracle_mod):
     """K^(0) = 0 (bri17.hpp:336-339, theory.rst:208-212): a right-hand side with a non-zero
     mean is projected, CG converges to the zero-mean solution instead of drifting."""
