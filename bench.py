@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--rs-steps", type=int, default=5)
     ap.add_argument("--cg-edge", type=int, default=512)
     ap.add_argument("--cg-max-iter", type=int, default=20000)
+    ap.add_argument("--rs-fault", default="", choices=["", "raise", "hang"],
+                    help="test aid: make the real-space records fail / hang, to check that the headline line still prints")
     ap.add_argument("--rs-timeout", type=float, default=900.0,
                     help="seconds after which the real-space / CG records are abandoned and the headline line is printed")
     return ap.parse_args()
@@ -105,7 +107,7 @@ class ClockSampler:
                 self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def __enter__(self):
         if self.nv:
@@ -589,6 +591,10 @@ def main():
         watchdog.daemon = True
         watchdog.start()
         try:
+            if args.rs_fault == "raise":
+                raise RuntimeError("injected fault (--rs-fault raise)")
+            if args.rs_fault == "hang":
+                time.sleep(10 ** 6)
             extra = realspace_records(args, torch, dist, local_rank, rank, world, dev)
         except BaseException as e:                    # e.g. a sticky CUDA error surfacing outside the records' own handlers
             extra = {"realspace": {"error": repr(e)}, "cg": None}

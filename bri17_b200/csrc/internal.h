@@ -106,6 +106,7 @@ struct bri17_plan {
   int sm_count = 0;
   bri17b200::AxisTables tab[3];
   int apply_variant = -1;  // -1: default
+  int solve_variant = 0;   // per-mode solves in 3-D: 1 = one mode per thread, <= 85 registers, 3 CTAs / SM (measured slower); 0 = default
   int mapping = 0;         // 0 auto, 1 always row tiles, 2 always flat tiles
   int64_t host_chunk_rows = 0;
   int host_streams = 3;

@@ -699,8 +699,8 @@ __device__ __forceinline__ AxisFactors axis_factors(const double *tab, int N, in
   return f;
 }
 
-template <int DIM, int MODE, int VEC>
-__global__ void __launch_bounds__(256, 2) modal_solve_kernel(const ApplyParams p) {
+template <int DIM, int MODE, int VEC, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) modal_solve_kernel(const ApplyParams p) {
   constexpr int THREADS = 256, TILE = THREADS * VEC;
   constexpr int NIN = MODE == 0 ? DIM : DIM * (DIM + 1) / 2;
   constexpr int NOUT = MODE == 2 ? DIM * (DIM + 1) / 2 : DIM;
@@ -1053,11 +1053,18 @@ int launch_modal_solve(bri17_plan *p, const Block &b, int mode, const void *in, 
   ap.f = static_cast<double2 *>(out);
   ap.u_stride = in_cs; ap.u_mstride = in_ms;
   ap.f_stride = out_cs; ap.f_mstride = out_ms;
-  // two modes per thread for the lighter maps (more loads in flight), one for eigenstress -> strain
-  const int vec = (mode == 0 || mode == 3 || (mode == 1 && b.dim == 2)) ? 2 : 1;   // register budget: no spills at 128
-  const int grid = make_geom(b, 256 * vec, p->sm_count * 2, &ap.g);
+  // Two modes per thread for the lighter maps (more loads in flight), one for eigenstress -> strain
+  // (register budget: no spills at 128).  Option "solve_variant" = 1 (3-D, K^-1 and eigenstress ->
+  // displacement): one mode per thread within 85 registers, three CTAs (24 warps) per SM instead of
+  // two -- MEASURED SLOWER (5600 vs 5648 and 4956 vs 5572 GB/s, profiles/r02_measurements.md), so
+  // these maps are not occupancy-bound either; kept as an option, off.
+  const bool dense = b.dim == 3 && p->solve_variant && (mode == 0 || mode == 1);
+  const int vec = dense ? 1 : ((mode == 0 || mode == 3 || (mode == 1 && b.dim == 2)) ? 2 : 1);
+  const int grid = make_geom(b, 256 * vec, p->sm_count * (dense ? 3 : 2), &ap.g);
   if (b.dim == 3) {
-    if (mode == 0) modal_solve_kernel<3, 0, 2><<<grid, 256, 0, stream>>>(ap);
+    if (mode == 0 && dense) modal_solve_kernel<3, 0, 1, 3><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 0) modal_solve_kernel<3, 0, 2><<<grid, 256, 0, stream>>>(ap);
+    else if (mode == 1 && dense) modal_solve_kernel<3, 1, 1, 3><<<grid, 256, 0, stream>>>(ap);
     else if (mode == 1) modal_solve_kernel<3, 1, 1><<<grid, 256, 0, stream>>>(ap);
     else if (mode == 2) modal_solve_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(ap);
     else modal_solve_kernel<3, 3, 2><<<grid, 256, 0, stream>>>(ap);

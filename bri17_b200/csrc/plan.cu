@@ -186,6 +186,8 @@ int bri17_plan_set_option(bri17_plan *p, const char *key, int64_t value) {
     if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "host_chunk_rows < 0");
     p->host_chunk_rows = value;
     free_host_stages(p);
+  } else if (!std::strcmp(key, "solve_variant")) {
+    p->solve_variant = value != 0;
   } else if (!std::strcmp(key, "host_zero_copy")) {
     p->host_zero_copy = value != 0;
     free_host_stages(p);
@@ -203,6 +205,7 @@ int bri17_plan_get_info(const bri17_plan *p, const char *key, int64_t *value) {
   if (!p || !key || !value) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
   if (!std::strcmp(key, "num_variants")) *value = num_variants();
   else if (!std::strcmp(key, "apply_variant")) *value = p->apply_variant < 0 ? default_variant(p) : p->apply_variant;
+  else if (!std::strcmp(key, "solve_variant")) *value = p->solve_variant;
   else if (!std::strcmp(key, "sm_count")) *value = p->sm_count;
   else if (!std::strcmp(key, "last_grid")) *value = p->last_grid.load();
   else if (!std::strcmp(key, "last_block")) *value = p->last_block.load();

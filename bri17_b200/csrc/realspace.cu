@@ -1613,11 +1613,11 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
   else if (!std::strcmp(key, "exchange_chunks")) {
     if (value < 0 || value > MAX_XCHUNKS) return fail(BRI17_ERR_INVALID_ARG, "exchange_chunks must be 0 (auto) .. 4");
     p->xchunks = int(value);
-  } else if (!std::strcmp(key, "fft_chunk_mib")) {
-    if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "fft_chunk_mib < 0");
+  } else if (!std::strcmp(key, "fft_chunk_mib") || !std::strcmp(key, "fft_chunk_planes")) {
+    if (value < 0) return fail(BRI17_ERR_INVALID_ARG, std::string(key) + " < 0");
     DeviceGuard guard(p->device);
     cudaDeviceSynchronize();
-    p->fft_chunk_mib = int(std::min<int64_t>(value, 1 << 20));
+    (key[10] == 'm' ? p->fft_chunk_mib : p->fft_chunk_planes) = int(std::min<int64_t>(value, 1 << 20));
     destroy_layout(p->lc);   // plans are rebuilt with the new chunk on next use
     destroy_layout(p->lr);
   } else if (!std::strcmp(key, "copy_ctas")) {

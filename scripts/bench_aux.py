@@ -43,11 +43,15 @@ del eps
 tau = torch.view_as_complex(torch.randn((6,) + shape + (2,), dtype=torch.float64, device="cuda"))
 ms = timed(lambda: op.eigenstress_to_opposite_strain(tau), 10)
 out["eigenstress_to_opposite_strain"] = {"ms": ms, "bytes_per_mode": 192, "gbs": 192 * M / ms / 1e6}
-ms = timed(lambda: op.eigenstress_to_displacement(tau), 10)
-out["eigenstress_to_displacement"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * M / ms / 1e6}
+for variant in (0, 1):      # 0: round-1 shapes (2 CTAs / SM, 128 registers); 1: one mode per thread, 3 CTAs / SM
+    op.set_option("solve_variant", variant)
+    ms = timed(lambda: op.eigenstress_to_displacement(tau), 10)
+    out[f"eigenstress_to_displacement_v{variant}"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * M / ms / 1e6}
 del tau
-ms = timed(lambda: op.solve_modal_stiffness(u), 10)
-out["modal_stiffness_solve"] = {"ms": ms, "bytes_per_mode": 96, "gbs": 96 * M / ms / 1e6}
+for variant in (0, 1):
+    op.set_option("solve_variant", variant)
+    ms = timed(lambda: op.solve_modal_stiffness(u), 10)
+    out[f"modal_stiffness_solve_v{variant}"] = {"ms": ms, "bytes_per_mode": 96, "gbs": 96 * M / ms / 1e6}
 slab = (edge, edge, edge)    # field writers on the whole grid (K^: 144 B/mode = 19.3 GB at 512^3)
 ms = timed(lambda: op.modal_stiffness_field(slab, (0, 0, 0)), 10)
 out["stiffness_field"] = {"ms": ms, "bytes_per_mode": 144, "gbs": 144 * M / ms / 1e6}
@@ -72,4 +76,10 @@ for name, mapping in (("rows", 1), ("flat", 2)):
     opf.set_option("mapping", mapping)
     ms = timed(lambda: opf.apply_modal_stiffness(uf, out=ff))
     out[f"apply_512^3_{name}"] = {"ms": ms, "gbs": 96 * M / ms / 1e6}
+# strong-scaling shards of the headline kernel on ONE GPU: what a rank of N = 2, 4, 8 runs (fixed costs only)
+for planes in (256, 128, 64):
+    us, fs = uf[:, :planes].contiguous(), ff[:, :planes].contiguous()
+    opf.set_option("mapping", 0)
+    ms = timed(lambda: opf.apply_modal_stiffness(us, out=fs, k_begin=(192, 0, 0)), 50)
+    out[f"apply_512^3_shard_{planes}_planes"] = {"ms": ms, "gbs": 96 * planes * edge * edge / ms / 1e6}
 print(json.dumps(out))
