@@ -445,7 +445,7 @@ struct bri17_rs_plan {
   int pipeline = 1;                               // overlap the exchange of component c with the FFTs of c+-1
   int fft_chunk_planes = 0;                       // same in planes (takes precedence; tests)
   int fft_chunk_mib = 0;                          // > 0: local 2-D transforms run in chunks of planes of this size (BatchFft); measured slower, off
-  int copy_ctas = 148 * 4;                        // grid cap of slab_copy_kernel
+  int copy_ctas = 0;                              // grid cap of slab_copy_kernel; 0 = copy_grid_cap() decides
   double2 *W = nullptr, *W2 = nullptr;  // exchange buffers, dim components of the c2c layout each
   size_t buf_bytes = 0;
   int64_t real_upper = 0;      // element offset of the upper region of W2 used by the real path
@@ -472,6 +472,18 @@ struct bri17_rs_plan {
 };
 
 namespace {
+
+// Grid cap of the exchange kernel.  Alone on the GPU it takes 4 CTAs per SM.  In the pipelined apply it
+// shares the SMs with cuFFT's kernels, and peer stores that wait for NVLink back up the memory pipeline of
+// every SM they are issued from: with 4 CTAs on every SM the "overlapped" time was the SUM of transform and
+// exchange.  Measured on 8 GPUs at 1024^3 (profiles/r02_measurements.md, ms per apply complex / real):
+// 592 CTAs 27.5 / 16.5, 296 -> 23.9 / 15.7, 148 -> 25.9 / 15.5, 96 -> 27.0 / 14.6, 64 -> 28.2 / 15.7.
+// The half spectrum moves half the bytes and needs fewer CTAs to keep NVLink busy.
+int copy_grid_cap(const bri17_rs_plan *p, const Layout &l, bool pipelined) {
+  if (p->copy_ctas > 0) return p->copy_ctas;
+  if (!pipelined) return p->sm_count * 4;
+  return l.real ? std::max(64, (p->sm_count * 2) / 3) : p->sm_count * 2;
+}
 
 int launch_copy(CopyPlan &cp, int fence, cudaStream_t st, int max_ctas) {
   long long per_seg = 0;
@@ -577,7 +589,7 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * (na >= 0 ? na : p->n0_loc) * P);
   if (p->mode == 1 && barriers) RS_TRY(stream_barrier(p, st));  // peers' buffers are free to overwrite
-  RS_TRY(launch_copy(cp, p->mode == 1, st, p->copy_ctas));
+  RS_TRY(launch_copy(cp, p->mode == 1, st, copy_grid_cap(p, l, !barriers)));
   if (P == 1) return BRI17_OK;
   if (p->mode == 1) return barriers ? stream_barrier(p, st) : BRI17_OK;   // everybody's stores have landed
   RS_NCCL_TRY(ncclGroupStart());
@@ -641,7 +653,7 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
     }
     cp.parts = choose_parts(l.n1_loc * S2e, (long long)ncomp * N0 / nchunks);
     if (barriers) RS_TRY(stream_barrier(p, st));
-    RS_TRY(launch_copy(cp, P > 1, st, p->copy_ctas));
+    RS_TRY(launch_copy(cp, P > 1, st, copy_grid_cap(p, l, !barriers)));
     return barriers ? stream_barrier(p, st) : BRI17_OK;
   }
   std::vector<long long> off(P + 1, 0);
@@ -687,7 +699,7 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
     g.dst_rs = (long long)S1 * S2e;
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * p->n0_loc * P);
-  return launch_copy(cp, 0, st, p->copy_ctas);
+  return launch_copy(cp, 0, st, copy_grid_cap(p, l, false));
 }
 
 // ---- chunked batched transforms (BatchFft) ---------------------------------------------------
@@ -1621,7 +1633,7 @@ int bri17_rs_plan_set_option(bri17_rs_plan *p, const char *key, int64_t value) {
     destroy_layout(p->lc);   // plans are rebuilt with the new chunk on next use
     destroy_layout(p->lr);
   } else if (!std::strcmp(key, "copy_ctas")) {
-    if (value < 1) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 1");
+    if (value < 0) return fail(BRI17_ERR_INVALID_ARG, "copy_ctas < 0");
     p->copy_ctas = int(value);
   } else return fail(BRI17_ERR_INVALID_ARG, std::string("unknown option ") + key);
   return BRI17_OK;

@@ -64,7 +64,8 @@ BRI17_API int bri17_rs_plan_destroy(bri17_rs_plan *plan);
  * "fft_chunk_mib" (> 0: run the local 2-D transforms in chunks of planes of this size so that
  * cuFFT's second kernel could hit L2; measured slower at every size, default 0 = whole slab;
  * "fft_chunk_planes": the same in planes),
- * "copy_ctas" (grid cap of the exchange kernel), "fused_axis0" (1 = run FFT(axis 0) ->
+ * "copy_ctas" (grid cap of the exchange kernel; 0 = default: 4 CTAs per SM when it runs alone, 2 per SM
+ * (complex) or 2/3 per SM (half spectrum) in the pipelined apply, where it shares the SMs with cuFFT), "fused_axis0" (1 = run FFT(axis 0) ->
  * K^ -> inverse FFT(axis 0) as one kernel when shape[0] is 16..1024 and a power of two;
  * default 1; 0 = cuFFT + modal kernel + cuFFT, the only path for other lengths),
  * "k1_major" (with the fused pass in 3-D, keep the Fourier-side block as [c][k1][n0][k2] so that
