@@ -74,6 +74,8 @@ RS_SIGNATURES = {
     "bri17_debug_axis0_fused_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                                _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
                                                C.c_int, C.c_int, _vp, _f64p]),
+    "bri17_debug_exchange_host": (C.c_int, [C.c_int, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
 }
 
 _lib = None

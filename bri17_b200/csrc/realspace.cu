@@ -541,7 +541,8 @@ int scalar_allreduce(bri17_rs_plan *p, double *v, int n, cudaStream_t st) {
 // the cross-GPU synchronisation to the caller (pipelined apply).
 // a0/na (mode 1 only): restrict the exchange to planes [a0, a0 + na) of this rank's n0 slab (na < 0: all).
 int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double2 *X, double2 *S, int ncomp,
-                     cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false, int a0 = 0, int na = -1) {
+                     cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false, int a0 = 0, int na = -1,
+                     CopyPlan *plan_only = nullptr) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   CopyPlan cp{};
   cp.ncomp = ncomp;
@@ -588,6 +589,7 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
     }
   }
   cp.parts = choose_parts(maxlen, (long long)ncomp * (na >= 0 ? na : p->n0_loc) * P);
+  if (plan_only) { *plan_only = cp; return BRI17_OK; }  // CPU replay of the index arithmetic (tests)
   if (p->mode == 1 && barriers) RS_TRY(stream_barrier(p, st));  // peers' buffers are free to overwrite
   RS_TRY(launch_copy(cp, p->mode == 1, st, copy_grid_cap(p, l, !barriers)));
   if (P == 1) return BRI17_OK;
@@ -614,7 +616,7 @@ int exchange_forward(bri17_rs_plan *p, const Layout &l, const double2 *T, double
 // destination's n0 slab (planes [n0q*chunk/nchunks, n0q*(chunk+1)/nchunks) of rank q).
 int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, double2 *D, double2 *R, int ncomp,
                       double scale, cudaStream_t st, int c0 = 0, bool barriers = true, bool xt = false,
-                      int chunk = 0, int nchunks = 1) {
+                      int chunk = 0, int nchunks = 1, CopyPlan *plan_only = nullptr) {
   const int P = p->nranks, r = p->rank, N0 = p->shape[0], S1 = l.S1, S2e = l.S2e;
   if (p->mode == 1 || P == 1) {
     // every row (c, n0) goes, whole, to the owner of n0, at its final position
@@ -652,6 +654,7 @@ int exchange_backward(bri17_rs_plan *p, const Layout &l, const double2 *X, doubl
       }
     }
     cp.parts = choose_parts(l.n1_loc * S2e, (long long)ncomp * N0 / nchunks);
+    if (plan_only) { *plan_only = cp; return BRI17_OK; }  // CPU replay (tests)
     if (barriers) RS_TRY(stream_barrier(p, st));
     RS_TRY(launch_copy(cp, P > 1, st, copy_grid_cap(p, l, !barriers)));
     return barriers ? stream_barrier(p, st) : BRI17_OK;
@@ -1747,6 +1750,63 @@ int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, int k1_beg
   a.out_scale = out_scale;
   a.herm_n = hermitian_n;
   return bri17b200::axis0::emulate(a, dim, dot_out);
+}
+
+// Test aid, HOST memory, no device needed: replays the fused exchange (mode 1) of `nranks` virtual ranks
+// on the CPU with the very CopyPlans the GPU path builds (exchange_forward / exchange_backward), executed by
+// a plain loop over their documented semantics.  direction 0: in[r] = local-transform layout of rank r,
+// [dim][n0_r][S1][S2e] -> out[q] = Fourier-side block of rank q ([dim][N0][n1_q][S2e], or k1-major
+// [dim][n1_q][N0][S2e]); direction 1: the way back.  real_layout: half spectrum of the last axis.
+// nchunks: sub-slabs per component, as in the pipelined apply.  Buffers hold complex128.
+int bri17_debug_exchange_host(int dim, const int *shape, int nranks, int real_layout, int k1_major, int nchunks,
+                              int direction, void *const *in, void *const *out) {
+  if (!shape || !in || !out) return fail(BRI17_ERR_INVALID_ARG, "NULL argument");
+  if ((dim != 2 && dim != 3) || nranks < 1 || nranks > MAX_RANKS || nchunks < 1 || nchunks > MAX_XCHUNKS)
+    return fail(BRI17_ERR_INVALID_ARG, "bad dim / nranks / nchunks");
+  auto run = [](const CopyPlan &cp) {
+    for (int si = 0; si < cp.nseg; si++) {
+      const CopySeg &g = cp.seg[si];
+      for (int c = 0; c < cp.ncomp; c++)
+        for (int a = 0; a < g.rows; a++)
+          for (int e = 0; e < g.len; e++) {
+            const long long so = (long long)(e / g.inner) * g.src_bs + e % g.inner;
+            const long long dd = (long long)(e / g.inner) * g.dst_bs + e % g.inner;
+            const double2 v = g.src[c * g.src_cs + a * g.src_rs + so];
+            g.dst[c * g.dst_cs + a * g.dst_rs + dd] = make_double2(v.x * cp.scale, v.y * cp.scale);
+          }
+    }
+  };
+  for (int r = 0; r < nranks; r++) {
+    bri17_rs_plan p;  // geometry only: no CUDA object is created or touched
+    p.dim = dim;
+    for (int d = 0; d < dim; d++) p.shape[d] = shape[d];
+    p.rank = r;
+    p.nranks = nranks;
+    p.mode = 1;
+    p.N2e = dim == 3 ? shape[2] : 1;
+    for (int q = 0; q <= nranks; q++) p.n0_beg[q] = int((int64_t)q * shape[0] / nranks);
+    p.n0_loc = p.n0_beg[r + 1] - p.n0_beg[r];
+    Layout l;
+    layout_geometry(&p, l, real_layout != 0);
+    const bool xt = k1_major && dim == 3;
+    for (int q = 0; q < nranks; q++) {
+      p.peerW[q] = static_cast<double2 *>(direction == 0 ? out[q] : in[q]);
+      p.peerW2[q] = static_cast<double2 *>(direction == 0 ? in[q] : out[q]);
+    }
+    for (int c = 0; c < dim; c++)
+      for (int j = 0; j < nchunks; j++) {
+        CopyPlan cp{};
+        if (direction == 0) {
+          const int a0 = int((long long)p.n0_loc * j / nchunks), a1 = int((long long)p.n0_loc * (j + 1) / nchunks);
+          RS_TRY(exchange_forward(&p, l, p.peerW2[r], p.peerW[r], nullptr, 1, nullptr, c, false, xt,
+                                  nchunks > 1 ? a0 : 0, nchunks > 1 ? a1 - a0 : -1, &cp));
+        } else {
+          RS_TRY(exchange_backward(&p, l, p.peerW[r], p.peerW2[r], nullptr, 1, 1.0, nullptr, c, false, xt, j, nchunks, &cp));
+        }
+        run(cp);
+      }
+  }
+  return BRI17_OK;
 }
 
 }  // extern "C"

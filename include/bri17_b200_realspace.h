@@ -170,6 +170,13 @@ BRI17_API int bri17_debug_axis0_fused_host(int dim, int N0, int64_t S, int S2e, 
                                            const double *tab2, double mu, double nu, double out_scale,
                                            int hermitian_n, int k1_major, void *X_host, double *dot_out);
 
+/* Test aid, HOST memory, no device needed: replays the fused all-to-all exchange of `nranks` virtual ranks on the
+ * CPU with the copy plans the GPU path builds.  direction 0: in[r] = [dim][n0_r][S1][S2e] (local-transform layout
+ * of rank r) -> out[q] = Fourier-side block of rank q, [dim][N0][n1_q][S2e] or, k1_major, [dim][n1_q][N0][S2e];
+ * direction 1: back.  real_layout: S = N/2+1 along the last axis.  nchunks: sub-slabs per component (1..4). */
+BRI17_API int bri17_debug_exchange_host(int dim, const int *shape, int nranks, int real_layout, int k1_major,
+                                        int nchunks, int direction, void *const *in, void *const *out);
+
 #ifdef __cplusplus
 }
 #endif
