@@ -1093,7 +1093,10 @@ int cg_core(bri17_rs_plan *p, Apply apply, const double *b, double *x, long long
 //   sx:    P0b P1b P2b                               Q0b Q1b Q2b
 int exchange_chunks(const bri17_rs_plan *p, const Layout &l) {
   if (p->xchunks > 0) return std::min(p->xchunks, MAX_XCHUNKS);
-  const long long bytes = 16ll * l.t_count;  // one component of the slab
+  // from the LARGEST slab of the decomposition, not this rank's own: every rank must come to the same
+  // count (one barrier per backward sub-slab), also when the slabs are uneven or some are empty
+  const long long planes = (p->shape[0] + p->nranks - 1) / p->nranks;
+  const long long bytes = 16ll * planes * l.S1 * l.S2e;  // one component of that slab
   return int(std::max<long long>(1, std::min<long long>(MAX_XCHUNKS, bytes >> 27)));  // >= 128 MiB per sub-slab
 }
 
