@@ -550,7 +550,9 @@ def main():
                 cpu = {"error": repr(e)}
         ws = modes_rank * 16 * dim
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (dim, edge) == (3, 512) else
+            f"Gmodes/s (fp64 modal stiffness apply, {dim}D {edge}^{dim}; NOT the BASELINE metric)",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(dim, edge, world),
