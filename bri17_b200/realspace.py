@@ -29,7 +29,7 @@ class RealSpaceOperator:
     """
 
     def __init__(self, shape, L, mu, nu, device=0, rank=0, world=1, unique_id: bytes | None = None,
-                 exchange_mode=EXCHANGE_NCCL):
+                 exchange_mode=EXCHANGE_PEER_STORE):
         self._lib = _lib.load_rs()
         self.shape, self.L = tuple(int(n) for n in shape), tuple(float(x) for x in L)
         self.dim, self.device, self.rank, self.world = len(shape), int(device), int(rank), int(world)
@@ -51,7 +51,7 @@ class RealSpaceOperator:
         self.exchange_bytes_real = int(self._lib.bri17_rs_plan_exchange_bytes(self._plan, 1))
 
     @classmethod
-    def from_process_group(cls, shape, L, mu, nu, device, exchange_mode=EXCHANGE_NCCL):
+    def from_process_group(cls, shape, L, mu, nu, device, exchange_mode=EXCHANGE_PEER_STORE):
         """Collective constructor: rank 0 draws the NCCL unique id and broadcasts
         it through the default torch.distributed group."""
         import torch.distributed as dist
